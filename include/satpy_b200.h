@@ -1,0 +1,193 @@
+/*
+ * satpy_b200.h -- C ABI of libsatpy_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary for satpy's per-pixel hot path.  satpy itself is
+ * pure Python and has no FFI for this path: the arithmetic lives inline in its
+ * Python file handlers / modifiers and in the pyresample / pykdtree / pyorbital
+ * wheels.  Each entry point below names the reference interface whose work it
+ * replaces (file:line under /root/reference/satpy unless stated), so a
+ * maintainer can bind it with ctypes.
+ *
+ * Conventions
+ *   - every pointer that is not marked "host" is a DEVICE pointer into memory
+ *     owned by the caller (e.g. torch.Tensor.data_ptr());
+ *   - sizes are int64_t, images are row-major (row 0 = northernmost line);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success, a B200_E* code otherwise, never
+ *     aborts and never prints; b200_last_error() gives the thread-local text;
+ *   - kernels are asynchronous on `stream`; nothing here synchronises except
+ *     where stated (grid build returns counts through a device->host copy).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns B200_ECUDA.
+ */
+#ifndef SATPY_B200_H
+#define SATPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_EINVAL 1   /* bad argument (maps to ValueError)          */
+#define B200_ECUDA 2    /* CUDA runtime error (maps to RuntimeError)  */
+#define B200_ENOMEM 3   /* allocation failed (maps to MemoryError)    */
+#define B200_EUNSUPPORTED 4 /* valid request this build cannot serve (NotImplementedError) */
+
+/* ------------------------------------------------------------------ geometry
+ * Projection + grid description, filled on the host by satpy_b200/geometry.py.
+ * Stands in for pyresample.geometry.AreaDefinition (+ pyproj) as used through
+ * area.get_lonlats() at modifiers/angles.py:434-441 and resample/kdtree.py:79-87.
+ */
+enum b200_proj_kind {
+    B200_PROJ_LONGLAT = 0,
+    B200_PROJ_EQC = 1,
+    B200_PROJ_MERC = 2,
+    B200_PROJ_GEOS = 3,
+    B200_PROJ_LAEA = 4,
+    B200_PROJ_LCC = 5,
+    B200_PROJ_STERE = 6
+};
+
+typedef struct b200_proj {
+    int32_t kind;   /* enum b200_proj_kind */
+    int32_t mode;   /* geos: 1 = sweep x; laea: 0 N,1 S,2 EQ,3 OB; stere: 0 north,1 south */
+    double a, es, e, one_es;
+    double lam0, phi0, x0, y0, k0;
+    double p[12];   /* kind-specific derived constants, see satpy_b200/geometry.py */
+} b200_proj_t;
+
+typedef struct b200_area {
+    b200_proj_t proj;
+    int64_t width, height;
+    double pixel_size_x, pixel_size_y; /* both positive */
+    double x_ul, y_ul;                 /* projection coords of the CENTRE of pixel (0,0) */
+} b200_area_t;
+
+/* A source/target geometry is either an area (lon/lat computed on device) or a
+ * swath (explicit lon/lat arrays, float64 or float32, degrees). */
+typedef struct b200_geo {
+    int32_t is_swath;      /* 0: use `area`; 1: use lons/lats                      */
+    int32_t lonlat_is_f32; /* swath arrays are float32 (else float64)              */
+    b200_area_t area;      /* used when !is_swath                                  */
+    const void *lons;      /* device, height*width                                 */
+    const void *lats;      /* device, height*width                                 */
+    int64_t width, height; /* grid shape (duplicates area.width/height for areas)  */
+    int64_t row0, nrows;   /* the row window [row0, row0+nrows) this call covers   */
+} b200_geo_t;
+
+/* ------------------------------------------------------------------ library */
+const char *b200_version(void);
+const char *b200_last_error(void);
+int b200_device_count(int *count /* host */);
+
+/* lon/lat of pixel centres, float64 degrees, +inf where the projection has no
+ * answer.  Replaces AreaDefinition.get_lonlats (modifiers/angles.py:438). */
+int b200_area_lonlats(const b200_geo_t *geo /* host */, double *lons, double *lats, void *stream);
+
+/* --------------------------------------------------------------- calibration
+ * ABI L1b: readers/core/abi.py:138-174 (_adjust_data) + readers/abi_l1b.py:133-173.
+ * mode 0 radiance, 1 reflectance [%], 2 brightness temperature [K].
+ */
+typedef struct b200_abi_cal {
+    int32_t mode;
+    int32_t is_unsigned;  /* _Unsigned == "true": reinterpret int16 as uint16      */
+    int32_t has_fill;
+    int32_t fill;         /* _FillValue as stored (int16 bit pattern, sign-extended) */
+    int32_t clip_negative_radiances;
+    float scale_factor, add_offset;
+    float refl_factor;    /* float32(pi * esd^2 / esun)                             */
+    float min_rad;        /* float32(ceil(-offset/scale)*scale+offset), abi_l1b.py:147-155 */
+    float fk1, fk2, bc1, bc2;
+} b200_abi_cal_t;
+
+int b200_abi_calibrate(const int16_t *counts, float *out, int64_t n,
+                       const b200_abi_cal_t *cal /* host */, void *stream);
+
+/* ------------------------------------------------------------- sun zenith
+ * get_cos_sza (modifiers/angles.py:418-469, pyorbital cos_zen) and
+ * _sunzen_corr_cos_ndarray (modifiers/angles.py:555-584) as driven by
+ * SunZenithCorrectorBase.__call__ (modifiers/geometry.py:48-71).
+ */
+typedef struct b200_sunz {
+    double gmst, ra, dec;     /* radians, from start_time (host, satpy_b200/modifiers/angles.py) */
+    double limit_deg;         /* correction_limit, default 88                        */
+    double max_sza_deg;       /* default 95                                          */
+    int32_t has_max_sza;      /* 0 => max_sza is None                                */
+    int32_t lonlat_f32;       /* 1 => lon/lat rounded to float32 first (float data)  */
+    int32_t method;           /* 0 SunZenithCorrector, 1 EffectiveSolarPathLength (utils.py:278-316) */
+    int32_t reserved;
+} b200_sunz_t;
+
+/* cos(sza) per pixel (float64, NaN off-disk); rows [geo->row0, +nrows). */
+int b200_cos_sza(const b200_geo_t *geo, const b200_sunz_t *sz, double *cos_sza, void *stream);
+
+/* out = data * corr(cos_sza(lon,lat)); lon/lat derived in-kernel from geo.
+ * nbands images of geo->nrows*width pixels, band stride = band_stride elements. */
+int b200_sunz_correct(const float *data, float *out, int32_t nbands, int64_t band_stride,
+                      const b200_geo_t *geo, const b200_sunz_t *sz, void *stream);
+
+/* Same, with the solar zenith angle given in degrees (optional_datasets branch,
+ * modifiers/geometry.py:64-66); sza is float32, one image shared by all bands. */
+int b200_sunz_correct_sza(const float *data, const float *sza_deg, float *out, int32_t nbands,
+                          int64_t band_stride, int64_t n, const b200_sunz_t *sz, void *stream);
+
+/* Fused reader calibration + SunZenithCorrector for up to 4 ABI reflective bands
+ * sharing one area: counts -> radiance -> reflectance[%] -> * corr.  6 B/pixel/band. */
+int b200_abi_vis_sunz(const int16_t *const *counts /* host array of device ptrs */,
+                      float *const *out /* host array of device ptrs */,
+                      const b200_abi_cal_t *cal /* host, nbands entries */, int32_t nbands,
+                      const b200_geo_t *geo, const b200_sunz_t *sz, void *stream);
+
+/* ---------------------------------------------------------------- nearest
+ * Replaces pyresample.kd_tree.XArrayResamplerNN.get_neighbour_info (kd-tree
+ * build + query; called from resample/kdtree.py:60-95) with a uniform
+ * grid-bucket search in spherical ECEF (R = 6370997 m), and
+ * get_sample_from_neighbour_info (resample/kdtree.py:184-190) with a gather.
+ */
+typedef struct b200_nn_grid b200_nn_grid_t; /* opaque, owned by the library */
+
+/* Build the bucket grid over the valid source points.
+ *   src            source geometry (whole grid: row0 = 0, nrows = height)
+ *   mask           optional uint8 (1 = exclude), src pixels; may be NULL
+ *   radius         radius_of_influence [m]
+ *   valid_input    out, uint8 src pixels (NN_COORDINATES "valid_input_index")
+ *   n_valid        out (host): number of valid source points
+ * Synchronises `stream` once (sizes come back to the host). */
+int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, double radius,
+                        uint8_t *valid_input, int64_t *n_valid /* host */,
+                        b200_nn_grid_t **grid /* host out */, void *stream);
+int b200_nn_grid_destroy(b200_nn_grid_t *grid);
+/* bytes of device memory held by the grid */
+int b200_nn_grid_nbytes(const b200_nn_grid_t *grid, int64_t *nbytes /* host */);
+
+/* Query k=1 for the target rows [dst->row0, +nrows).
+ *   index_array    out int32, compressed valid-input index, -1 = no neighbour
+ *                  (NN_COORDINATES "index_array", z2 = 1); may be NULL
+ *   gather_index   out int32, RAW flat source pixel index, -1 = none; may be NULL
+ *   valid_output   out uint8 ("valid_output_index"); may be NULL */
+int b200_nn_query(const b200_nn_grid_t *grid, const b200_geo_t *dst, double radius,
+                  int32_t *index_array, int32_t *gather_index, uint8_t *valid_output,
+                  void *stream);
+
+/* out[b][i] = gather_index[i] < 0 ? fill : data[b][gather_index[i]]
+ * elem_size in {1,2,4,8}; fill points at one host element of that size. */
+int b200_nn_gather(const void *data, void *out, const int32_t *gather_index, int64_t n_out,
+                   int32_t nbands, int64_t src_band_stride, int64_t dst_band_stride,
+                   int32_t elem_size, const void *fill /* host */, void *stream);
+
+/* Fused query + gather (no index materialised): float32 data only. */
+int b200_nn_query_gather_f32(const b200_nn_grid_t *grid, const b200_geo_t *dst, double radius,
+                             const float *data, float *out, int32_t nbands,
+                             int64_t src_band_stride, int64_t dst_band_stride, float fill,
+                             void *stream);
+
+/* compressed index -> raw flat index (and back) helpers for cached index arrays */
+int b200_nn_compressed_to_raw(const uint8_t *valid_input, int64_t n_src, const int32_t *index_array,
+                              int32_t *gather_index, int64_t n_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATPY_B200_H */

@@ -510,8 +510,11 @@ class Area:
             cols = np.arange(self.width)
         if rows is None:
             rows = np.arange(self.height)
-        x = self.area_extent[0] + (np.asarray(cols, dtype=np.float64) + 0.5) * self.pixel_size_x
-        y = self.area_extent[3] - (np.asarray(rows, dtype=np.float64) + 0.5) * self.pixel_size_y
+        # pyresample ``AreaDefinition._get_proj_vectors``: arange(n) * pixel_size + pixel_upper_left
+        x_ul = self.area_extent[0] + self.pixel_size_x / 2.0
+        y_ul = self.area_extent[3] - self.pixel_size_y / 2.0
+        x = np.asarray(cols, dtype=np.float64) * self.pixel_size_x + x_ul
+        y = np.asarray(rows, dtype=np.float64) * -self.pixel_size_y + y_ul
         return x, y
 
     def get_lonlats(self, row_slice: slice | None = None):

@@ -1,0 +1,73 @@
+"""Oracle end-to-end pipeline (numpy / scipy) -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of the chain the benchmark times on the device (configs 2 and 5):
+``NC_ABI_L1B.get_dataset`` (satpy/readers/abi_l1b.py:45-72) -> ``SunZenithCorrector.__call__``
+(satpy/modifiers/geometry.py:48-71) -> ``KDTreeResampler.precompute`` / ``.compute``
+(satpy/resample/kdtree.py:60-95,184-190).  Used by tests, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``; never by ``satpy_b200``.
+"""
+from __future__ import annotations
+
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import calibration, nearest, solar
+from .projections import Area
+
+
+def make_area(params) -> Area:
+    proj, w, h, ext = params
+    return Area(proj, w, h, ext)
+
+
+def abi_reflectance(counts, band):
+    return calibration.abi_calibrate(counts, "reflectance", band["scale_factor"], band["add_offset"],
+                                     band["fill_value"], band.get("unsigned", False), esun=band["esun"],
+                                     esd=band["earth_sun_distance_anomaly_in_AU"])
+
+
+def abi_sunz(counts, band, src: Area, start_time, row_slice=None):
+    """calibrate + sun-zenith correct (float32)."""
+    refl = abi_reflectance(counts, band)
+    return solar.sun_zenith_corrector(refl, src, start_time, row_slice=row_slice)
+
+
+def _row_blocks(n_rows, width, itemsize=4, chunk_bytes=32 << 20):
+    """Row blocks of about 32 MiB, the reference benchmarks' dask chunk size (benchmarks/abi_l1b_benchmarks.py:52)."""
+    rows = max(1, int(chunk_bytes // (width * itemsize)))
+    return [slice(r, min(n_rows, r + rows)) for r in range(0, n_rows, rows)]
+
+
+def abi_sunz_threaded(counts, band, src: Area, start_time, workers=None):
+    """Same as ``abi_sunz`` over ~32 MiB row blocks on a thread pool (stand-in for dask's threaded scheduler)."""
+    workers = workers or len(os.sched_getaffinity(0))
+    out = np.empty(counts.shape, dtype=np.float32)
+    blocks = _row_blocks(counts.shape[0], counts.shape[1])
+
+    def work(sl):
+        out[sl] = abi_sunz(counts[sl], band, src, start_time, row_slice=sl)
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(work, blocks))
+    return out
+
+
+def abi_sunz_nearest(counts, band, src_params, dst_params, start_time, radius, dst_rows: slice | None = None,
+                     workers=-1, timings: dict | None = None):
+    """The whole chain; ``dst_rows`` restricts the target to a row window (bounded CPU samples)."""
+    src, dst = make_area(src_params), make_area(dst_params)
+    t0 = time.perf_counter()
+    data = abi_sunz_threaded(counts, band, src, start_time)
+    t1 = time.perf_counter()
+    slon, slat = src.get_lonlats()
+    dlon, dlat = dst.get_lonlats(dst_rows)
+    t2 = time.perf_counter()
+    valid_in, valid_out, index = nearest.get_neighbour_info(slon, slat, dlon, dlat, radius, workers=workers)
+    t3 = time.perf_counter()
+    out = nearest.get_sample_from_neighbour_info(data, valid_in, index, np.float32(np.nan))
+    t4 = time.perf_counter()
+    if timings is not None:
+        timings.update(calibrate_sunz=t1 - t0, lonlats=t2 - t1, search=t3 - t2, gather=t4 - t3)
+    return out

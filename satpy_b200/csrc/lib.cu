@@ -1,0 +1,97 @@
+// Library-level entry points of libsatpy_b200.so: version, thread-local error text,
+// device probing and the lon/lat helper (AreaDefinition.get_lonlats stand-in,
+// satpy/modifiers/angles.py:438).
+#include <stdarg.h>
+#include "b200_common.cuh"
+#include "b200_proj.cuh"
+
+static thread_local char g_err[512] = "";
+
+void b200_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *b200_version(void) { return "satpy_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char *b200_last_error(void) { return g_err; }
+
+extern "C" int b200_device_count(int *count) {
+    B200_CHECK_ARG(count != nullptr, "count is NULL");
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        *count = 0;
+        b200_set_error("b200_device_count: %s", cudaGetErrorString(err));
+        return B200_ECUDA;
+    }
+    *count = n;
+    return B200_OK;
+}
+
+int b200_check_geo(const b200_geo_t *geo, const char *who) {
+    if (geo == nullptr) {
+        b200_set_error("%s: geometry is NULL", who);
+        return B200_EINVAL;
+    }
+    if (geo->width <= 0 || geo->height <= 0) {
+        b200_set_error("%s: empty geometry (%lld x %lld)", who, (long long)geo->height, (long long)geo->width);
+        return B200_EINVAL;
+    }
+    if (geo->row0 < 0 || geo->nrows < 0 || geo->row0 + geo->nrows > geo->height) {
+        b200_set_error("%s: row window [%lld, +%lld) outside the %lld-row grid", who, (long long)geo->row0,
+                       (long long)geo->nrows, (long long)geo->height);
+        return B200_EINVAL;
+    }
+    if (geo->is_swath) {
+        if (geo->lons == nullptr || geo->lats == nullptr) {
+            b200_set_error("%s: swath geometry without lon/lat arrays", who);
+            return B200_EINVAL;
+        }
+    } else {
+        int k = geo->area.proj.kind;
+        if (k < B200_PROJ_LONGLAT || k > B200_PROJ_STERE) {
+            b200_set_error("%s: unknown projection kind %d", who, k);
+            return B200_EINVAL;
+        }
+        if (!(geo->area.pixel_size_x > 0.0) || !(geo->area.pixel_size_y > 0.0)) {
+            b200_set_error("%s: pixel sizes must be positive", who);
+            return B200_EINVAL;
+        }
+    }
+    return B200_OK;
+}
+
+struct GeoArg {
+    b200_geo_t g;
+};
+
+__global__ void __launch_bounds__(256)
+area_lonlats_kernel(double *__restrict__ lons, double *__restrict__ lats, const __grid_constant__ GeoArg A) {
+    const int64_t W = A.g.width;
+    const int64_t n = A.g.nrows * W;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int64_t r = i / W;
+        double lon, lat;
+        b200_geo_lonlat(A.g, A.g.row0 + r, i - r * W, lon, lat);
+        lons[i] = lon;
+        lats[i] = lat;
+    }
+}
+
+extern "C" int b200_area_lonlats(const b200_geo_t *geo, double *lons, double *lats, void *stream) {
+    int rc = b200_check_geo(geo, "b200_area_lonlats");
+    if (rc) return rc;
+    int64_t n = geo->nrows * geo->width;
+    if (n == 0) return B200_OK;
+    B200_CHECK_ARG(lons != nullptr && lats != nullptr, "NULL output");
+    GeoArg A;
+    A.g = *geo;
+    area_lonlats_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(lons, lats, A);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

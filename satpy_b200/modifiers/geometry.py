@@ -1,0 +1,197 @@
+"""``SunZenithCorrector`` / ``EffectiveSolarPathLengthCorrector`` on the device.
+
+Host-side mirror of satpy/modifiers/geometry.py:34-160: same class names, same
+constructor keywords (``max_sza=95.0``, ``correction_limit=88.0``), same call
+convention ``modifier([vis] or [vis, sza], optional_datasets=[...], **info)``,
+same ``sunz_corrected`` short-circuit (:52-54), same ``IncompatibleAreas`` error
+when the inputs live on different areas (satpy/tests/test_modifiers.py:178-184),
+attrs copied and ``modifiers`` updated like ``apply_modifier_info``
+(satpy/composites/core.py:99-125).
+
+The arithmetic -- ``get_cos_sza`` (satpy/modifiers/angles.py:418-469), the
+``max_sza`` mask (geometry.py:62-63) and ``_sunzen_corr_cos_ndarray``
+(angles.py:555-584) or ``atmospheric_path_length_correction``
+(satpy/utils.py:278-316) -- is ONE kernel launch (csrc/sunz.cu); lon/lat never
+touch HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import numpy as np
+
+from .. import _lib
+from ..dataset import is_dataarray, payload, rewrap
+from ..geometry import as_geometry
+from .astronomy import solar_scalars
+
+logger = logging.getLogger(__name__)
+
+
+class IncompatibleAreas(Exception):
+    """Same role as satpy.composites.core.IncompatibleAreas (composites/core.py:41)."""
+
+
+def _sunz_struct(start_time, limit, max_sza, lonlat_f32, method):
+    s = _lib.SunzStruct()
+    if start_time is None:
+        s.gmst = s.ra = s.dec = 0.0
+    else:
+        s.gmst, s.ra, s.dec = solar_scalars(start_time)
+    s.limit_deg = float(limit)
+    s.has_max_sza = 0 if max_sza is None else 1
+    s.max_sza_deg = 0.0 if max_sza is None else float(max_sza)
+    s.lonlat_f32 = 1 if lonlat_f32 else 0
+    s.method = int(method)
+    s.reserved = 0
+    return s
+
+
+def _to_cuda_f32(torch, data):
+    was_numpy = not isinstance(data, torch.Tensor)
+    if was_numpy:
+        a = np.ascontiguousarray(data)
+        if a.dtype != np.float32:
+            raise TypeError(f"the device sun-zenith correction works on float32 data, got {a.dtype}")
+        return torch.from_numpy(a).to("cuda", non_blocking=True), True
+    if data.dtype != torch.float32:
+        raise TypeError(f"the device sun-zenith correction works on float32 data, got {data.dtype}")
+    return (data if data.is_cuda else data.to("cuda")).contiguous(), False
+
+
+def cos_sza(area, start_time, lonlat_f32=True, row_slice=None, device=False):
+    """cos(solar zenith angle) per pixel, float64, NaN where the area has no lon/lat.
+
+    ``get_cos_sza`` (satpy/modifiers/angles.py:418-431) with the reference's dtype flow:
+    lon/lat rounded to float32 when the data is float32 (``lonlat_f32``).
+    """
+    torch = _lib.require_cuda()
+    area = as_geometry(area)
+    rows = range(area.height)[row_slice] if row_slice is not None else range(area.height)
+    row0, nrows = (rows.start, len(rows)) if len(rows) else (0, 0)
+    out = torch.empty((nrows, area.width), dtype=torch.float64, device="cuda")
+    g = area.geo_struct(row0, nrows)
+    s = _sunz_struct(start_time, 88.0, None, lonlat_f32, 0)
+    _lib.check(_lib.load().b200_cos_sza(C.byref(g), C.byref(s), out.data_ptr(), _lib.stream_ptr(torch)))
+    return out if device else out.cpu().numpy()
+
+
+def sunz_correct(data, area=None, start_time=None, correction_limit=88.0, max_sza=95.0, sza=None,
+                 method="cos", row0=0, out=None):
+    """Apply the sun-zenith correction to ``data`` (``(y, x)`` or ``(bands, y, x)`` float32).
+
+    Either ``area`` + ``start_time`` (angles derived on the device) or ``sza`` (degrees, float32,
+    the ``optional_datasets`` branch of satpy/modifiers/geometry.py:64-66).  ``row0``: first area row
+    that ``data`` covers (row-tiled multi-GPU use).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
+    """
+    torch = _lib.require_cuda()
+    t, was_numpy = _to_cuda_f32(torch, data)
+    if t.dim() not in (2, 3):
+        raise ValueError("data must be (y, x) or (bands, y, x)")
+    nbands = 1 if t.dim() == 2 else t.shape[0]
+    h, w = t.shape[-2:]
+    if out is None:
+        out = torch.empty_like(t)
+    meth = {"cos": 0, "effective_path_length": 1}[method]
+    lib = _lib.load()
+    if sza is None:
+        if area is None or start_time is None:
+            raise ValueError("need either (area, start_time) or sza")
+        area = as_geometry(area)
+        if w != area.width or row0 + h > area.height:
+            raise IncompatibleAreas(f"data shape {(h, w)} (row offset {row0}) does not fit area shape {area.shape}")
+        g = area.geo_struct(row0, h)
+        s = _sunz_struct(start_time, correction_limit, max_sza, True, meth)
+        _lib.check(lib.b200_sunz_correct(t.data_ptr(), out.data_ptr(), nbands, h * w, C.byref(g), C.byref(s),
+                                         _lib.stream_ptr(torch)))
+    else:
+        z, _ = _to_cuda_f32(torch, sza)
+        if tuple(z.shape) != (h, w):
+            raise IncompatibleAreas(f"sza shape {tuple(z.shape)} != data shape {(h, w)}")
+        s = _sunz_struct(None, correction_limit, max_sza, True, meth)
+        _lib.check(lib.b200_sunz_correct_sza(t.data_ptr(), z.data_ptr(), out.data_ptr(), nbands, h * w, h * w,
+                                             C.byref(s), _lib.stream_ptr(torch)))
+    return out.cpu().numpy() if was_numpy else out
+
+
+class _SunZenithCorrectorBase:
+    """``SunZenithCorrectorBase`` (satpy/modifiers/geometry.py:34-74) without the xarray/dask machinery."""
+
+    _method = "cos"
+
+    def __init__(self, max_sza=95.0, **kwargs):
+        self.max_sza = max_sza
+        self.max_sza_cos = np.cos(np.deg2rad(max_sza)) if max_sza is not None else None
+        # ModifierBase/CompositeBase keep every other keyword (name, prerequisites, _satpy_id, ...) in attrs
+        self.attrs = dict(kwargs)
+
+    def _limit(self):
+        return 88.0
+
+    @staticmethod
+    def _check_areas(arrays):
+        areas = [a.attrs.get("area") for a in arrays if is_dataarray(a)]
+        if any(a is None for a in areas) and not all(a is None for a in areas):
+            raise ValueError("Missing 'area' attribute")
+        shapes = {tuple(payload(a).shape[-2:]) for a in arrays}
+        if len(shapes) > 1:
+            raise IncompatibleAreas("All areas should be of the same size: %s" % sorted(shapes))
+        for a in areas[1:]:
+            if a is not None and a != areas[0]:
+                raise IncompatibleAreas("Areas are different")
+
+    def __call__(self, projectables, optional_datasets=None, **info):
+        optional = [d for d in (optional_datasets or []) if d is not None]
+        arrays = list(projectables) + list(optional)
+        self._check_areas(arrays)
+        vis = arrays[0]
+        if vis.attrs.get("sunz_corrected"):
+            logger.debug("Sun zenith correction already applied")
+            return vis
+        logger.debug("Applying sun zen correction")
+        if len(arrays) < 2:
+            res = sunz_correct(payload(vis), area=vis.attrs["area"], start_time=vis.attrs["start_time"],
+                               correction_limit=self._limit(), max_sza=self.max_sza, method=self._method)
+        else:
+            res = sunz_correct(payload(vis), sza=payload(arrays[1]), correction_limit=self._limit(),
+                               max_sza=self.max_sza, method=self._method)
+        proj = rewrap(vis, res, attrs=dict(vis.attrs))
+        self.apply_modifier_info(vis, proj)
+        return proj
+
+    def apply_modifier_info(self, origin, destination):
+        """satpy/composites/core.py:99-125 for the default key set."""
+        o, d = origin.attrs, destination.attrs
+        for k in ("name", "modifiers"):
+            if k == "modifiers" and k in self.attrs:
+                d[k] = self.attrs[k]
+            elif d.get(k) is None:
+                if self.attrs.get(k) is not None:
+                    d[k] = self.attrs[k]
+                elif o.get(k) is not None:
+                    d[k] = o[k]
+
+
+class SunZenithCorrector(_SunZenithCorrectorBase):
+    """Standard ``1 / cos(sunz)`` correction with the log fall-off between ``correction_limit`` and ``max_sza``."""
+
+    def __init__(self, correction_limit=88., **kwargs):
+        self.correction_limit = correction_limit
+        super().__init__(**kwargs)
+
+    def _limit(self):
+        return self.correction_limit
+
+
+class EffectiveSolarPathLengthCorrector(_SunZenithCorrectorBase):
+    """Li & Shibata (2006) effective path length correction (satpy/modifiers/geometry.py:121-163)."""
+
+    _method = "effective_path_length"
+
+    def __init__(self, correction_limit=88., **kwargs):
+        self.correction_limit = correction_limit
+        super().__init__(**kwargs)
+
+    def _limit(self):
+        return self.correction_limit

@@ -1,0 +1,130 @@
+"""The BASELINE.json hot path end to end on one GPU: ABI counts -> reflectance -> sun-zenith
+correction -> nearest-neighbour resampling (configs 2 and 5).
+
+This is the chain ``Scene.load([C02], modifiers=("sunz_corrected",))`` + ``Scene.resample(area,
+resampler="nearest")`` evaluates lazily in the reference (SURVEY.md sections 3.1-3.3):
+``NC_ABI_L1B.get_dataset`` (satpy/readers/abi_l1b.py:45-72) -> ``SunZenithCorrector.__call__``
+(satpy/modifiers/geometry.py:48-71) -> ``KDTreeResampler.precompute/compute``
+(satpy/resample/kdtree.py:60-95,184-190).  Here it is three kernel families on one stream:
+fused calibrate+sunz (6 B/pixel), bucket-grid build, fused query+gather (or query once + gather).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .geometry import as_geometry
+from .modifiers.geometry import _sunz_struct
+from .resample.nearest import _Grid
+
+
+class ABIResamplePipeline:
+    """Reusable device state for resampling a stream of ABI images between two fixed geometries."""
+
+    def __init__(self, src_area, dst_area, radius_of_influence, row_window=None):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.src = as_geometry(src_area)
+        self.dst = as_geometry(dst_area)
+        self.radius = float(radius_of_influence)
+        self.row0, self.nrows = (0, self.dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
+        torch = self.torch
+        self.refl = torch.empty(self.src.shape, dtype=torch.float32, device="cuda")
+        self.valid_input = torch.empty(self.src.shape, dtype=torch.uint8, device="cuda")
+        self.grid = None
+        self.gather_index = None
+        self.n_valid = None
+        self.launches = 0
+
+    @property
+    def out_shape(self):
+        return (self.nrows, self.dst.width)
+
+    # ------------------------------------------------------------------ stages
+    def calibrate_sunz(self, counts_dev, cal, start_time, correction_limit=88.0, max_sza=95.0):
+        """counts (int16, device) -> sun-zenith-corrected reflectance [%] in ``self.refl``; one launch."""
+        torch = self.torch
+        s_cal = (_lib.AbiCalStruct * 1)(cal.struct("reflectance"))
+        g = self.src.geo_struct()
+        sz = _sunz_struct(start_time, correction_limit, max_sza, True, 0)
+        cptr = (C.c_void_p * 1)(counts_dev.data_ptr())
+        optr = (C.c_void_p * 1)(self.refl.data_ptr())
+        _lib.check(self.lib.b200_abi_vis_sunz(cptr, optr, s_cal, 1, C.byref(g), C.byref(sz), _lib.stream_ptr(torch)))
+        self.launches += 1
+        return self.refl
+
+    def build_grid(self):
+        """Bucket grid over the valid source points (4 launches + 2 cub scans)."""
+        torch = self.torch
+        self.grid = None
+        n_valid = C.c_int64(0)
+        handle = C.c_void_p(None)
+        gs = self.src.geo_struct()
+        _lib.check(self.lib.b200_nn_grid_create(C.byref(gs), None, self.radius, self.valid_input.data_ptr(),
+                                                C.byref(n_valid), C.byref(handle), _lib.stream_ptr(torch)))
+        self.grid = _Grid(handle)
+        self.n_valid = int(n_valid.value)
+        self.launches += 2
+        return self.grid
+
+    def query_gather(self, data, out, fill=float("nan")):
+        """Fused search + gather of float32 ``data`` into ``out``; one launch."""
+        torch = self.torch
+        gd = self.dst.geo_struct(self.row0, self.nrows)
+        _lib.check(self.lib.b200_nn_query_gather_f32(self.grid.handle, C.byref(gd), self.radius, data.data_ptr(),
+                                                     out.data_ptr(), 1, self.src.size, out.numel(), fill,
+                                                     _lib.stream_ptr(torch)))
+        self.launches += 1
+        return out
+
+    def query(self):
+        """Search once and keep the gather index on the device (the cached-neighbour-info mode)."""
+        torch = self.torch
+        self.gather_index = torch.empty(self.out_shape, dtype=torch.int32, device="cuda")
+        gd = self.dst.geo_struct(self.row0, self.nrows)
+        _lib.check(self.lib.b200_nn_query(self.grid.handle, C.byref(gd), self.radius, None,
+                                          self.gather_index.data_ptr(), None, _lib.stream_ptr(torch)))
+        self.launches += 1
+        return self.gather_index
+
+    def gather(self, data, out, fill=float("nan")):
+        torch = self.torch
+        fill_buf = (C.c_char * 4).from_buffer_copy(np.float32(fill).tobytes())
+        _lib.check(self.lib.b200_nn_gather(data.data_ptr(), out.data_ptr(), self.gather_index.data_ptr(),
+                                           out.numel(), 1, self.src.size, out.numel(), 4,
+                                           C.cast(fill_buf, C.c_void_p), _lib.stream_ptr(torch)))
+        self.launches += 1
+        return out
+
+    # --------------------------------------------------------------------- step
+    def run(self, counts_dev, cal, start_time, out=None, reuse_neighbours=False):
+        """One pass of the hot path.  ``reuse_neighbours``: keep the index arrays of the previous pass
+        (what ``cache_dir`` / ``resamplers_cache`` give the reference for fixed geostationary grids)."""
+        torch = self.torch
+        if out is None:
+            out = torch.empty(self.out_shape, dtype=torch.float32, device="cuda")
+        self.calibrate_sunz(counts_dev, cal, start_time)
+        if reuse_neighbours:
+            if self.gather_index is None:
+                self.build_grid()
+                self.query()
+                self.grid = None
+            return self.gather(self.refl, out)
+        self.build_grid()
+        self.query_gather(self.refl, out)
+        return out
+
+
+def abi_sunz_nearest(counts, cal, src_area, dst_area, start_time, radius_of_influence, row_window=None):
+    """Convenience wrapper: host or device counts in, device float32 image out."""
+    torch = _lib.require_cuda()
+    t = counts if isinstance(counts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(counts))
+    if t.dtype == torch.uint16:
+        t = t.view(torch.int16)
+    t = t.to("cuda", non_blocking=True).contiguous()
+    pipe = ABIResamplePipeline(src_area, dst_area, radius_of_influence, row_window)
+    out = pipe.run(t, cal, start_time)
+    torch.cuda.current_stream().synchronize()
+    return out

@@ -1,0 +1,405 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run with ``-m gpu`` on a B200.
+
+Bars: bit-exact for integer / index work (equidistant ties counted and bounded), <= 1e-5 relative for
+float32 values (north_star), exact equality for the reference's golden vectors where numpy is exact.
+"""
+import datetime as dt
+
+import numpy as np
+import pytest
+
+from oracle import calibration as ocal
+from oracle import nearest as onn
+from oracle import solar as osolar
+from oracle.projections import Area as OArea
+from oracle.projections import Swath as OSwath
+from satpy_b200 import AreaDefinition, DataArrayLite, SwathDefinition, demo
+from satpy_b200.modifiers import EffectiveSolarPathLengthCorrector, IncompatibleAreas, SunZenithCorrector, cos_sza
+from satpy_b200.modifiers import sunz_correct
+from satpy_b200.readers import ABICalibration, calibrate_abi
+from satpy_b200.resample import B200NearestResampler
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5  # north_star: resampled and calibrated float32 values within 1e-5 relative
+
+
+def both_areas(name, scale=1.0):
+    params = demo.area_params(name, scale)
+    return demo.make_area(name, scale), OArea(*params)
+
+
+# ---------------------------------------------------------------------------------- calibration
+def test_abi_ir_golden_vector():
+    """satpy/tests/reader_tests/test_abi_l1b.py:207-225,391-414."""
+    shape = (750, 1250)
+    rad = (np.arange(shape[0] * shape[1]).reshape(shape) + 1.0) * 50.0
+    rad[0, 0] = -0.0001
+    counts = ((rad + 1.3) / 0.5).astype(np.int16)
+    fill = np.int16(np.floor(((9 + 1) * 50.0 + 1.3) / 0.5))
+    for clip, first in ((False, np.nan), (True, 134.68753)):
+        cal = ABICalibration(scale_factor=0.5, add_offset=-1.3, fill_value=fill, planck_fk1=13432.1,
+                             planck_fk2=1497.61, planck_bc1=0.09102, planck_bc2=0.99971,
+                             clip_negative_radiances=clip)
+        res = calibrate_abi(counts, cal, "brightness_temperature")
+        assert res.dtype == np.float32
+        expected = np.array([first, 304.97037, 332.22778, 354.6147, 374.08688, 391.58655, 407.64786, 422.60635,
+                             436.68802, np.nan])
+        np.testing.assert_allclose(res[0, :10], expected, equal_nan=True, atol=1e-4)
+        ref = ocal.abi_calibrate(counts, "brightness_temperature", 0.5, -1.3, fill, fk1=13432.1, fk2=1497.61,
+                                 bc1=0.09102, bc2=0.99971, clip_negative_radiances=clip)
+        np.testing.assert_allclose(res, ref, rtol=REL, equal_nan=True)
+
+
+def test_abi_vis_golden_vector():
+    """satpy/tests/reader_tests/test_abi_l1b.py:48-70,423-443."""
+    shape = (1500, 2500)
+    rad = (np.arange(shape[0] * shape[1]).reshape(shape) + 1.0) * 50.0
+    counts = ((rad + 1.0) / 0.5).astype(np.int16)
+    cal = ABICalibration(scale_factor=0.5, add_offset=-1.0, fill_value=1002, esun=2017,
+                         earth_sun_distance_anomaly_in_AU=0.99)
+    res = calibrate_abi(counts, cal, "reflectance")
+    expected = np.array([7.632808, 15.265616, 22.898426, 30.531233, 38.164043, 45.796852, 53.429657, 61.062466,
+                         68.695274, np.nan])
+    np.testing.assert_allclose(res[0, :10], expected, equal_nan=True)
+    ref = ocal.abi_calibrate(counts, "reflectance", 0.5, -1.0, 1002, esun=2017, esd=0.99)
+    np.testing.assert_array_equal(res, ref)  # float32 mul/add in the reference's order: bit-exact
+    rad_dev = calibrate_abi(counts, cal, "radiance")
+    np.testing.assert_array_equal(rad_dev, ocal.abi_calibrate(counts, "radiance", 0.5, -1.0, 1002))
+
+
+@pytest.mark.parametrize("band,calibration", [("C01", "reflectance"), ("C02", "reflectance"), ("C02", "radiance"),
+                                              ("C13", "brightness_temperature")])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4099, 1 << 20])
+def test_abi_calibrate_sizes(band, calibration, n):
+    """Ragged sizes exercise the vector body and the scalar tail; unsigned counts with fill values."""
+    counts = demo.abi_counts((n,), seed=11 + n % 7, band=band, fill_fraction=0.01)
+    b = demo.ABI_BANDS[band]
+    cal = demo.abi_calibration(band)
+    res = calibrate_abi(counts, cal, calibration)
+    kw = {k: b[k] for k in ("esun",) if k in b}
+    if "earth_sun_distance_anomaly_in_AU" in b:
+        kw["esd"] = b["earth_sun_distance_anomaly_in_AU"]
+    for k in ("fk1", "fk2", "bc1", "bc2"):
+        if "planck_" + k in b:
+            kw[k] = b["planck_" + k]
+    ref = ocal.abi_calibrate(counts, calibration, b["scale_factor"], b["add_offset"], b["fill_value"], b["unsigned"],
+                             **kw)
+    assert res.shape == ref.shape and res.dtype == np.float32
+    if calibration == "brightness_temperature":
+        np.testing.assert_allclose(res, ref, rtol=REL, equal_nan=True)
+    else:
+        np.testing.assert_array_equal(res, ref)
+
+
+def test_abi_calibrate_errors():
+    cal = demo.abi_calibration("C02")
+    with pytest.raises(ValueError):
+        calibrate_abi(np.zeros(4, np.int16), cal, "albedo")
+    with pytest.raises(TypeError):
+        calibrate_abi(np.zeros(4, np.float32), cal, "radiance")
+    with pytest.raises(ValueError):
+        calibrate_abi(np.zeros(4, np.int16), demo.abi_calibration("C13"), "reflectance")
+
+
+# ------------------------------------------------------------------------------------ geometry
+PROJ_CASES = [
+    ("geos_y", {"proj": "geos", "lon_0": 0.0, "a": 6378169.0, "b": 6356583.8, "h": 35785831.0}, 120, 120,
+     (-5570248.68, -5567248.28, 5567248.28, 5570248.68)),
+    ("geos_x", {"proj": "geos", "sweep": "x", "lon_0": -75.0, "h": 35786023.0, "ellps": "GRS80"}, 130, 110,
+     (-5434894.885056, -5434894.885056, 5434894.885056, 5434894.885056)),
+    ("eqc", {"proj": "eqc", "lon_0": 10.0, "ellps": "WGS84"}, 100, 80, (-2.0e7, -1.0e7, 2.0e7, 1.0e7)),
+    ("merc", {"proj": "merc"}, 90, 70, (-1.5e7, -1.2e7, 1.5e7, 1.2e7)),
+    ("merc_ts_sphere", {"proj": "merc", "lat_ts": 30.0, "R": 6371000.0}, 64, 64, (-1.0e7, -8.0e6, 1.0e7, 8.0e6)),
+    ("laea_ob", {"proj": "laea", "lat_0": 52.0, "lon_0": 10.0, "x_0": 4321000.0, "y_0": 3210000.0, "ellps": "GRS80"},
+     100, 90, (2500000.0, 1400000.0, 7500000.0, 5900000.0)),
+    ("laea_n", {"proj": "laea", "lat_0": 90.0, "lon_0": 0.0, "ellps": "WGS84"}, 80, 80, (-5e6, -5e6, 5e6, 5e6)),
+    ("laea_s_sphere", {"proj": "laea", "lat_0": -90.0, "lon_0": 20.0, "R": 6371228.0}, 80, 80, (-5e6, -5e6, 5e6, 5e6)),
+    ("laea_eq", {"proj": "laea", "lat_0": 0.0, "lon_0": -30.0, "ellps": "WGS84"}, 80, 80, (-6e6, -6e6, 6e6, 6e6)),
+    ("lcc", {"proj": "lcc", "lat_1": 30.0, "lat_2": 60.0, "lat_0": 38.0, "lon_0": 126.0, "ellps": "WGS84"}, 100, 100,
+     (-3.0e6, -3.0e6, 3.0e6, 3.0e6)),
+    ("lcc_1sp", {"proj": "lcc", "lat_1": 25.0, "lat_0": 25.0, "lon_0": -95.0, "datum": "WGS84"}, 60, 60,
+     (-2.0e6, -2.0e6, 2.0e6, 2.0e6)),
+    ("stere_n", {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 0.0, "ellps": "WGS84"}, 100, 100,
+     (-4.0e6, -4.0e6, 4.0e6, 4.0e6)),
+    ("stere_s", {"proj": "stere", "lat_0": -90.0, "lat_ts": -71.0, "lon_0": 0.0, "ellps": "WGS84"}, 100, 100,
+     (-4.0e6, -4.0e6, 4.0e6, 4.0e6)),
+    ("longlat", {"proj": "longlat", "datum": "WGS84"}, 72, 36, (-180.0, -90.0, 180.0, 90.0)),
+]
+
+
+@pytest.mark.parametrize("name,proj,w,h,ext", PROJ_CASES, ids=[c[0] for c in PROJ_CASES])
+def test_area_lonlats_match_oracle(name, proj, w, h, ext):
+    """Device inverse projections vs the oracle (float64): < 1e-9 degrees, same off-earth pattern."""
+    area = AreaDefinition(name, name, name, proj, w, h, ext)
+    lons, lats = area.get_lonlats()
+    olons, olats = OArea(proj, w, h, ext).get_lonlats()
+    assert lons.shape == (h, w)
+    fin = np.isfinite(olons)
+    np.testing.assert_array_equal(np.isfinite(lons), fin)
+    dlon = np.abs(lons[fin] - olons[fin])
+    dlon = np.minimum(dlon, 360.0 - dlon)
+    assert dlon.max() < 1e-9
+    assert np.abs(lats[fin] - olats[fin]).max() < 1e-9
+    # row windows address the same pixels
+    lons_w, lats_w = area.get_lonlats(slice(3, 11))
+    np.testing.assert_array_equal(lons_w, lons[3:11])
+    np.testing.assert_array_equal(lats_w, lats[3:11])
+
+
+# ---------------------------------------------------------------------------------- sun zenith
+def _sunz_area():
+    return AreaDefinition("test", "test", "test", {"proj": "merc"}, 2, 2, (-2000, -2000, 2000, 2000))
+
+
+def test_cos_sza_golden():
+    """cos(SZA) fixture of satpy/tests/test_modifiers.py:104."""
+    cz = cos_sza(_sunz_area(), dt.datetime(2018, 1, 1, 18), lonlat_f32=False)
+    np.testing.assert_allclose(cz, [[0.0149581333, 0.0146694376], [0.0150812684, 0.0147925727]], rtol=2e-8)
+
+
+def test_sunz_corrector_golden_not_provided():
+    """satpy/tests/test_modifiers.py:116-146 (float32 branch)."""
+    attrs = {"area": _sunz_area(), "start_time": dt.datetime(2018, 1, 1, 18), "modifiers": tuple(), "name": "test_vis"}
+    ds = DataArrayLite(np.ones((2, 2), dtype=np.float32), ("y", "x"), attrs)
+    comp = SunZenithCorrector(name="sza_test", modifiers=tuple())
+    res = comp((ds,), test_attr="test")
+    assert res.dtype == np.float32
+    np.testing.assert_allclose(res.values, np.array([[22.401667, 22.31777], [22.437503, 22.353533]]), rtol=1e-6)
+    # apply_modifier_info only fills keys the data does not have yet (satpy/composites/core.py:99-125)
+    assert res.attrs["area"] is attrs["area"] and res.attrs["name"] == "test_vis"
+    assert res.attrs["modifiers"] == tuple()
+    comp = SunZenithCorrector(name="sza_test", modifiers=tuple(), correction_limit=90)
+    res = comp((ds,), test_attr="test")
+    np.testing.assert_allclose(res.values, np.array([[66.853262, 68.168939], [66.30742, 67.601493]]), rtol=1e-5)
+
+
+def test_sunz_corrector_golden_provided():
+    """satpy/tests/test_modifiers.py:148-176: SZA given as an optional dataset."""
+    area = _sunz_area()
+    attrs = {"area": area, "start_time": dt.datetime(2018, 1, 1, 18), "modifiers": tuple(), "name": "test_vis"}
+    ds = DataArrayLite(np.ones((2, 2), dtype=np.float32), ("y", "x"), attrs)
+    sza = np.rad2deg(np.arccos(np.array([[0.0149581333, 0.0146694376], [0.0150812684, 0.0147925727]])))
+    sza = DataArrayLite(sza.astype(np.float32), ("y", "x"), {"area": area})
+    res = SunZenithCorrector(name="sza_test", modifiers=tuple())((ds, sza), test_attr="test")
+    np.testing.assert_allclose(res.values, np.array([[22.401667, 22.31777], [22.437503, 22.353533]], np.float32),
+                               rtol=1e-5)
+    res = SunZenithCorrector(name="sza_test", modifiers=tuple(), correction_limit=90)((ds, sza))
+    np.testing.assert_allclose(res.values, np.array([[66.853262, 68.168939], [66.30742, 67.601493]]), rtol=1e-5)
+    # already corrected -> returned untouched (satpy/modifiers/geometry.py:52-54)
+    ds2 = DataArrayLite(np.ones((2, 2), dtype=np.float32), ("y", "x"), dict(attrs, sunz_corrected=True))
+    assert SunZenithCorrector(name="x")((ds2,)) is ds2
+
+
+def test_sunz_incompatible_areas():
+    """satpy/tests/test_modifiers.py:178-184."""
+    big = AreaDefinition("test", "test", "test", {"proj": "merc"}, 4, 4, (-2000, -2000, 2000, 2000))
+    ds2 = DataArrayLite(np.ones((4, 4), dtype=np.float32), ("y", "x"),
+                        {"area": big, "start_time": dt.datetime(2018, 1, 1, 18)})
+    sza = DataArrayLite(np.ones((2, 2), dtype=np.float32), ("y", "x"), {"area": _sunz_area()})
+    with pytest.raises(IncompatibleAreas):
+        SunZenithCorrector(name="sza_test", modifiers=tuple())((ds2, sza))
+
+
+def _assert_sunz_close(res, ref):
+    """1e-5 relative, with an absolute floor where the fall-off drives the corrected value to zero."""
+    assert res.shape == ref.shape
+    np.testing.assert_array_equal(np.isnan(res), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.maximum(np.abs(ref[ok]), 1e-2 * np.nanmax(np.abs(ref)) * 1e-3 + 1e-3)
+    err = np.abs(res[ok] - ref[ok]) / scale
+    assert err.max() <= REL, f"max scaled error {err.max():.3e}"
+
+
+@pytest.mark.parametrize("areaname,scale,when", [
+    ("goes_east_abi_f_2km", 700 / 5424, dt.datetime(2019, 3, 14, 18, 0)),     # day
+    ("goes_east_abi_f_2km", 700 / 5424, dt.datetime(2019, 3, 14, 23, 30)),    # terminator on the disk
+    ("msg_seviri_fes_3km", 600 / 3712, dt.datetime(2020, 6, 21, 5, 0)),
+])
+@pytest.mark.parametrize("max_sza,limit", [(95.0, 88.0), (None, 88.0), (90.0, 80.0)])
+def test_sunz_correct_matches_oracle(areaname, scale, when, max_sza, limit):
+    area, oarea = both_areas(areaname, scale)
+    rng = np.random.default_rng(5)
+    data = rng.uniform(0, 120, size=area.shape).astype(np.float32)
+    data[rng.random(area.shape) < 0.01] = np.nan
+    res = sunz_correct(data, area=area, start_time=when, correction_limit=limit, max_sza=max_sza)
+    ref = osolar.sun_zenith_corrector(data, oarea, when, correction_limit=limit, max_sza=max_sza)
+    assert res.dtype == np.float32
+    _assert_sunz_close(res, ref)
+    # multi-band input shares the factor
+    res3 = sunz_correct(np.stack([data, data * 2]), area=area, start_time=when, correction_limit=limit,
+                        max_sza=max_sza)
+    np.testing.assert_array_equal(res3[0], res)
+    # a row window gives the same pixels (row-tiled multi-GPU use)
+    resw = sunz_correct(data[100:164], area=area, start_time=when, correction_limit=limit, max_sza=max_sza, row0=100)
+    np.testing.assert_array_equal(resw, res[100:164])
+
+
+def test_effective_path_length_matches_oracle():
+    area, oarea = both_areas("goes_east_abi_f_2km", 500 / 5424)
+    when = dt.datetime(2019, 3, 14, 22, 0)
+    data = np.random.default_rng(6).uniform(0, 100, size=area.shape).astype(np.float32)
+    ds = DataArrayLite(data, ("y", "x"), {"area": area, "start_time": when, "name": "C02"})
+    res = EffectiveSolarPathLengthCorrector(name="eff")((ds,)).values
+    cz = osolar.get_cos_sza(oarea, when, np.float32)
+    with np.errstate(invalid="ignore"):
+        cz = np.where(cz >= np.cos(np.deg2rad(95.0)), cz, np.nan)
+    ref = osolar.atmospheric_path_length_correction(data, cz).astype(np.float32)
+    _assert_sunz_close(res, ref)
+
+
+def test_fused_abi_vis_sunz_matches_oracle():
+    from satpy_b200.pipeline import ABIResamplePipeline
+    import torch
+    scale = 900 / 10848
+    area, oarea = both_areas("goes_east_abi_f_1km", scale)
+    counts = demo.abi_counts(area.shape, seed=7, band="C02")
+    pipe = ABIResamplePipeline(area, demo.make_area("global_eqc_500m", 64 / 80150), 5e4)
+    res = pipe.calibrate_sunz(torch.from_numpy(counts).cuda(), demo.abi_calibration("C02"), demo.START_TIME)
+    res = res.cpu().numpy()
+    from oracle import reference_pipeline as rp
+    ref = rp.abi_sunz(counts, demo.ABI_BANDS["C02"], oarea, demo.START_TIME)
+    _assert_sunz_close(res, ref)
+
+
+# ------------------------------------------------------------------------------------- nearest
+def _check_indices(resampler, o_src, o_dst, radius, mask=None, max_tie_frac=2e-3):
+    info = resampler.neighbour_info()
+    slon, slat = o_src.get_lonlats()
+    dlon, dlat = o_dst.get_lonlats()
+    vin, vout, idx = onn.get_neighbour_info(slon, slat, dlon, dlat, radius, mask=mask)
+    n_valid = int(vin.sum())
+    np.testing.assert_array_equal(info["valid_input_index"], vin)
+    np.testing.assert_array_equal(info["valid_output_index"], vout)
+    ref = onn.to_minus_one(idx, n_valid)[..., 0]
+    got = info["index_array"][..., 0]
+    assert got.shape == ref.shape and got.dtype == np.int32
+    n_mis, n_tie, n_bad = onn.compare_indices(got, ref, slon, slat, dlon, dlat, vin)
+    assert n_bad == 0, f"{n_bad} index mismatches that are not equidistant ties (of {n_mis})"
+    assert n_tie <= max_tie_frac * got.size + 8, f"{n_tie} ties of {got.size}"
+    return vin, ref, got, n_tie
+
+
+NN_CASES = [
+    # (source area, scale, target area, scale, radius [m])
+    ("msg_seviri_fes_3km", 300 / 3712, "euro_laea_1km", 400 / 5000, 50000.0),     # config 1 geometry
+    ("goes_east_abi_f_2km", 400 / 5424, "goes_east_eqc_2km", 500 / 9050, 40000.0),  # config 2 geometry
+    ("goes_east_abi_f_1km", 500 / 10848, "global_eqc_500m", 900 / 80150, 30000.0),  # config 5 geometry
+    ("goes_east_abi_f_1km", 300 / 10848, "global_eqc_500m", 300 / 80150, 5000.0),   # radius << pixel: many misses
+]
+
+
+@pytest.mark.parametrize("sname,sscale,dname,dscale,radius", NN_CASES)
+def test_nearest_indices_match_oracle(sname, sscale, dname, dscale, radius):
+    src, o_src = both_areas(sname, sscale)
+    dst, o_dst = both_areas(dname, dscale)
+    r = B200NearestResampler(src, dst)
+    r.precompute(radius_of_influence=radius)
+    vin, ref, got, n_tie = _check_indices(r, o_src, o_dst, radius)
+    # gather parity for several dtypes, including multi-band
+    rng = np.random.default_rng(3)
+    for dtype, fill in ((np.float32, np.nan), (np.float64, np.nan), (np.int16, -999), (np.uint8, 255)):
+        data = (rng.uniform(0, 200, size=(2,) + src.shape)).astype(dtype)
+        out = r.compute(data, fill_value=fill)
+        assert out.dtype == dtype and out.shape == (2,) + dst.shape
+        idx3 = np.where(got < 0, int(vin.sum()), got)[..., None]
+        exp = onn.get_sample_from_neighbour_info(data, vin, idx3, fill)
+        np.testing.assert_array_equal(out, exp)
+
+
+def test_nearest_fused_equals_two_step():
+    src, _ = both_areas("goes_east_abi_f_1km", 400 / 10848)
+    dst, _ = both_areas("global_eqc_500m", 700 / 80150)
+    data = np.random.default_rng(1).uniform(0, 100, size=src.shape).astype(np.float32)
+    r = B200NearestResampler(src, dst)
+    two = r.resample(data, radius_of_influence=40000.0)
+    fused = r.resample_fused(data, 40000.0)
+    np.testing.assert_array_equal(two, fused)
+    # row windows tile the target exactly
+    parts = [r.resample_fused(data, 40000.0, row_window=(r0, n)) for r0, n in ((0, 100), (100, 150), (250, dst.height - 250))]
+    np.testing.assert_array_equal(np.concatenate(parts), two)
+    # cached neighbour info is reused and can be re-installed from the reference-layout arrays
+    info = r.neighbour_info()
+    r2 = B200NearestResampler(src, dst)
+    r2.load_neighbour_info(info["valid_input_index"], info["index_array"].astype(np.int64))
+    np.testing.assert_array_equal(r2.compute(data), two)
+
+
+def test_nearest_swath_golden_2x2():
+    """The only un-mocked nearest case of the reference: satpy/tests/test_resample.py:109-129."""
+    lons = np.arange(4).reshape((2, 2))
+    source = SwathDefinition(lons, lons)
+    dest = SwathDefinition(lons + .0001, lons + .0001)
+    expected_gap = np.array([[1, 2], [3, 255]])
+    data = DataArrayLite(expected_gap, ("y", "x"), {"_FillValue": 255, "area": source})
+    res = B200NearestResampler(source, dest).resample(data, fill_value=255)
+    assert res.dtype == expected_gap.dtype
+    assert np.all(res.values == expected_gap)
+    res = B200NearestResampler(source, dest).resample(data, fill_value=255, radius_of_influence=1000000)
+    assert np.all(res.values == np.array([[1, 2], [3, 3]]))
+    assert res.attrs["area"] is dest
+
+
+def test_nearest_swath_source_with_mask_and_dateline():
+    """Swath source crossing the antimeridian and the pole region, NaN data masked like BaseResampler.resample."""
+    rng = np.random.default_rng(9)
+    h, w = 220, 180
+    lat = np.linspace(60, 89.5, h)[:, None] + rng.uniform(-0.02, 0.02, (h, w))
+    lon = ((np.linspace(150, 215, w)[None, :] + rng.uniform(-0.02, 0.02, (h, w)) + 180) % 360) - 180
+    data = rng.uniform(0, 1, (h, w)).astype(np.float32)
+    data[rng.random((h, w)) < 0.05] = np.nan
+    src = SwathDefinition(lon, lat)
+    dst, o_dst = both_areas("euro_laea_1km", 1.0)
+    dst = AreaDefinition("ps", "ps", "ps", {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 180.0,
+                                            "ellps": "WGS84"}, 200, 200, (-2.5e6, -2.5e6, 2.5e6, 2.5e6))
+    o_dst = OArea(dst.proj_dict, 200, 200, dst.area_extent)
+    radius = 30000.0
+    r = B200NearestResampler(src, dst)
+    out = r.resample(data, radius_of_influence=radius)
+    mask = np.isnan(data)
+    vin, ref, got, _ = _check_indices(r, OSwath(lon, lat), o_dst, radius, mask=mask)
+    idx3 = np.where(ref < 0, int(vin.sum()), ref)[..., None]
+    exp = onn.get_sample_from_neighbour_info(data, vin, idx3, np.float32(np.nan))
+    same = (got == ref)
+    np.testing.assert_array_equal(out[same], exp[same])
+    assert np.isfinite(out).sum() > 1000
+
+
+def test_nearest_float32_swath_and_empty_results():
+    lon = np.linspace(-10, 10, 50, dtype=np.float32)[None, :].repeat(40, 0)
+    lat = np.linspace(40, 50, 40, dtype=np.float32)[:, None].repeat(50, 1)
+    src = SwathDefinition(lon, lat)
+    far = AreaDefinition("far", "far", "far", {"proj": "eqc", "lon_0": 0.0, "ellps": "WGS84"}, 30, 20,
+                         (1.0e7, -5.0e6, 1.5e7, -4.0e6))
+    r = B200NearestResampler(src, far)
+    out = r.resample(np.ones((40, 50), np.float32), radius_of_influence=20000.0, mask_area=False)
+    assert np.isnan(out).all()
+    assert (r.neighbour_info()["index_array"] == -1).all()
+    with pytest.raises(ValueError):
+        r.precompute(radius_of_influence=-5.0)
+    with pytest.raises(ValueError):
+        r.compute(np.ones((3, 3), np.float32))
+
+
+# ------------------------------------------------------------------------------------ pipeline
+def test_pipeline_matches_oracle_and_cached_mode():
+    import torch
+    from oracle import reference_pipeline as rp
+    from satpy_b200.pipeline import ABIResamplePipeline
+    s, d = 700 / 10848, 1400 / 80150
+    src, dst = demo.make_area("goes_east_abi_f_1km", s), demo.make_area("global_eqc_500m", d)
+    counts = demo.abi_counts(src.shape, seed=7, band="C02")
+    radius = 2.5 * 1002.0 / s
+    pipe = ABIResamplePipeline(src, dst, radius)
+    cdev = torch.from_numpy(counts).cuda()
+    out = pipe.run(cdev, demo.abi_calibration("C02"), demo.START_TIME).cpu().numpy()
+    out2 = pipe.run(cdev, demo.abi_calibration("C02"), demo.START_TIME, reuse_neighbours=True).cpu().numpy()
+    np.testing.assert_array_equal(out, out2)
+    ref = rp.abi_sunz_nearest(counts, demo.ABI_BANDS["C02"], demo.area_params("goes_east_abi_f_1km", s),
+                              demo.area_params("global_eqc_500m", d), demo.START_TIME, radius)
+    nan_mismatch = (np.isnan(out) != np.isnan(ref)).mean()
+    assert nan_mismatch < 1e-5
+    ok = ~np.isnan(out) & ~np.isnan(ref)
+    err = np.abs(out[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-3)
+    # ties may pick the other of two equidistant pixels: bounded, everything else within 1e-5
+    assert (err > REL).mean() < 2e-3
