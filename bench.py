@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the satpy hot path on B200: ABI C02 full disk calibrate + sun-zenith + nearest resample.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scale S]
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on; it fits one GPU):
+synthetic ABI C02 10848 x 10848 int16 counts on ``goes_east_abi_f_1km`` -> reflectance [%] ->
+SunZenithCorrector -> nearest-neighbour to the 0.5 km global equirectangular grid 80150 x 40075
+(3212 Mpix, 12.85 GB float32), radius_of_influence 2000 m.  One "step" is one full pass:
+fused calibrate+sunz kernel, bucket-grid build, fused query+gather, (N > 1) one NCCL all-gather.
+With N GPUs the target is cut into N row tiles, each rank working on the source rows that can reach
+its tile (strong scaling: the total work is fixed).
+
+One JSON line is printed by rank 0 (see the keys in ``main``).  ``value`` is whole-job output Mpix/s
+with inputs resident in HBM; ``e2e`` is the same through the public host-buffer API with the
+host<->device copies inside the timed region.  ``--impl reference`` times the CPU oracle (numpy/scipy
+restatement of the satpy/pyresample path -- satpy itself cannot be installed in this image, see
+DESIGN.md) on a bounded sample of the same workload with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "output Mpix/s, ABI full-disk nearest resample+sunz"
+UNIT = "Mpix/s"
+SRC_AREA, DST_AREA, BAND, SEED, RADIUS = "goes_east_abi_f_1km", "global_eqc_500m", "C02", 7, 2000.0
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink both grids (debugging only; 1.0 = the named workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(scale):
+    from satpy_b200 import demo
+    sp, dp = demo.area_params(SRC_AREA, scale), demo.area_params(DST_AREA, scale)
+    radius = RADIUS / scale
+    return sp, dp, radius
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ---------------------------------------------------------------------------- CPU reference arm
+CPU_TILE_ROWS_FRAC = 1.0 / 256.0
+CPU_TILE_AT = (1 / 8, 3 / 8, 5 / 8, 7 / 8)
+
+
+class CpuSample:
+    """Bounded sample of the workload for the CPU path: 4 target row tiles (1/256 of the rows each, at 1/8, 3/8,
+    5/8 and 7/8 of the height) with the source row bands that can reach them."""
+
+    def __init__(self, counts, sp, dp, radius):
+        from oracle import reference_pipeline as rp
+        from satpy_b200 import demo
+        self.rp, self.sp, self.dp, self.radius = rp, sp, dp, radius
+        self.band = demo.ABI_BANDS[BAND]
+        self.start_time = demo.START_TIME
+        src, dst = rp.make_area(sp), rp.make_area(dp)
+        n = max(1, int(round(dst.height * CPU_TILE_ROWS_FRAC)))
+        self.tiles = []
+        for frac in CPU_TILE_AT:
+            r0 = min(dst.height - n, int(dst.height * frac))
+            rows = slice(r0, r0 + n)
+            srows = rp.source_rows_for_tile(src, dst, rows, radius)
+            self.tiles.append((rows, srows, np.ascontiguousarray(counts[srows])))
+        self.mpix = sum((t[0].stop - t[0].start) * dst.width for t in self.tiles) / 1e6
+        self.describe = (f"{len(self.tiles)} target row tiles of {n} rows at "
+                         f"{'/'.join(f'{f:.3f}' for f in CPU_TILE_AT)} of the height ({self.mpix:.1f} Mpix of "
+                         f"{dst.width * dst.height / 1e6:.0f}) with their source row bands "
+                         f"({sum(t[2].shape[0] for t in self.tiles)} of {src.height} rows); numpy+scipy.cKDTree "
+                         f"restatement of the satpy/pyresample path, not satpy itself")
+
+    def step(self, timings=None):
+        for rows, srows, cnt in self.tiles:
+            if cnt.shape[0] == 0:
+                continue
+            self.rp.abi_sunz_nearest(cnt, self.band, self.sp, self.dp, self.start_time, self.radius, dst_rows=rows,
+                                     src_rows=srows, workers=-1, timings=timings)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from satpy_b200 import demo
+    sp, dp, radius = workload_config(args.scale)
+    counts = demo.abi_counts((sp[2], sp[1]), SEED, BAND)
+    sample = CpuSample(counts, sp, dp, radius)
+    cores = len(os.sched_getaffinity(0))
+    for _ in range(args.warmup):
+        sample.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sample.step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = sample.mpix / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(sp, dp, radius, args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample.describe},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(sp, dp, radius, args):
+    return {"workload": f"configs[4]: synthetic ABI {BAND} {sp[1]}x{sp[2]} full-disk ({SRC_AREA}) calibrate+sunz+nearest "
+                        f"-> {dp[1]}x{dp[2]} {DST_AREA}, radius_of_influence {radius:g} m, row tiles over {args.gpus} GPU(s)",
+            "source_shape": [sp[2], sp[1]], "target_shape": [dp[2], dp[1]], "radius_m": radius, "seed": SEED,
+            "l2": "inputs and outputs larger than L2 (no flush needed)" if args.scale >= 0.5 else "debug scale",
+            "scale": args.scale, "parallelism": f"row-tiles x{args.gpus} + all-gather" if args.gpus > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from satpy_b200 import _lib, demo, parallel
+    from satpy_b200.pipeline import ABIResamplePipeline
+
+    _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: satpy_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    sp, dp, radius = workload_config(args.scale)
+    src, dst = demo.make_area(SRC_AREA, args.scale), demo.make_area(DST_AREA, args.scale)
+    cal = demo.abi_calibration(BAND)
+    counts = demo.abi_counts(src.shape, SEED, BAND)
+
+    tile_rows, tiles = parallel.row_tiles(dst.height, world)
+    row0, nrows = tiles[rank]
+    s_row0, s_nrows = (0, src.height) if world == 1 else parallel.source_row_window(src, dst, row0, nrows, radius)
+    pipe = ABIResamplePipeline(src, dst, radius, row_window=(row0, nrows), src_row_window=(s_row0, s_nrows))
+    counts_win = np.ascontiguousarray(counts[s_row0:s_row0 + s_nrows])
+    counts_pin = torch.from_numpy(counts_win).pin_memory() if s_nrows else torch.empty((0, src.width), dtype=torch.int16)
+    counts_dev = counts_pin.cuda()
+    full = torch.empty((world * tile_rows, dst.width), dtype=torch.float32, device="cuda")
+    mine = full[rank * tile_rows: rank * tile_rows + nrows]
+
+    def step():
+        pipe.run(counts_dev, cal, demo.START_TIME, out=mine)
+        if world > 1:
+            parallel.all_gather_rows(full, tile_rows, rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / max(1, steps)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = pipe.launches
+    ms_step = timed(step, args.steps)
+    launches = (pipe.launches - launches0)
+    clocks = sampler.stop() if sampler else None
+    n_out_total = dst.width * dst.height
+    value = n_out_total / 1e6 / (ms_step / 1e3)
+
+    # ---- per-stage device times on this rank (CUDA events on the launching stream)
+    stages = {}
+    if nrows and s_nrows:
+        n_src_win = s_nrows * src.width
+        n_out_tile = nrows * dst.width
+
+        def stage(name, fn, bytes_alg):
+            for _ in range(2):
+                fn()
+            ms = timed_local(torch, fn, args.steps)
+            stages[name] = {"ms": ms, "algorithmic_bytes": bytes_alg, "gbs": bytes_alg / ms / 1e6}
+        stage("abi_vis_sunz_kernel", lambda: pipe.calibrate_sunz(counts_dev, cal, demo.START_TIME), 6 * n_src_win)
+        stage("nn_grid_create", pipe.build_grid, 0)
+        n_valid = pipe.n_valid
+        stage("nn_query_gather_f32_kernel", lambda: pipe.query_gather(pipe.refl, mine), 4 * n_out_tile + 4 * n_valid)
+        stage("nn_query_kernel", pipe.query, 4 * n_out_tile)
+        stage("nn_gather_kernel", lambda: pipe.gather(pipe.refl, mine), 8 * n_out_tile + 4 * n_valid)
+        pipe.gather_index = None
+        torch.cuda.empty_cache()
+
+    # ---- e2e: public host-buffer API, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        out_pin = torch.empty((nrows, dst.width), dtype=torch.float32, pin_memory=True)
+
+        def step_host():
+            pipe.run_host(counts_pin, cal, demo.START_TIME, out_pin, out_dev=mine)
+        for _ in range(2):
+            step_host()
+        ms_e2e = timed(step_host, max(2, min(args.steps, 3)))
+        e2e = {"value": n_out_total / 1e6 / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(counts_pin.numel() * 2), "d2h_bytes_per_step": int(out_pin.numel() * 4),
+               "note": "per rank: pinned counts -> device, pipeline, own tile -> pinned host; bytes are per rank"}
+        del out_pin
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    roofline = None
+    if stages:
+        kernels = {k: v for k, v in stages.items() if k in ("abi_vis_sunz_kernel", "nn_query_gather_f32_kernel")}
+        top = max(kernels, key=lambda k: kernels[k]["ms"])
+        roofline = {"kernel": top, "bound": "hbm", "achieved": stages[top]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": stages[top]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": stages[top]["ms"] / ms_step,
+                    "note": "algorithmic bytes / CUDA-event time of the dominant kernel on rank 0; see profiles/ for ncu"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 values / f64 geometry", "data": "synthetic",
+            "config": config_dict(sp, dp, radius, args), "clocks": clocks, "gpu_launches": launches,
+            "roofline": roofline, "stages": stages, "e2e": e2e}
+
+    if world == 1 and not args.no_cpu_baseline:
+        sample = CpuSample(counts, sp, dp, radius)
+        cores = len(os.sched_getaffinity(0))
+        sample.step()
+        tm = {}
+        t0 = time.perf_counter()
+        sample.step(tm)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample.mpix / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": sample.describe, "seconds": dt, "stage_seconds": tm}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def timed_local(torch, fn, steps):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / max(1, steps)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,8 +149,11 @@ int b200_abi_vis_sunz(const int16_t *const *counts /* host array of device ptrs 
 typedef struct b200_nn_grid b200_nn_grid_t; /* opaque, owned by the library */
 
 /* Build the bucket grid over the valid source points.
- *   src            source geometry (whole grid: row0 = 0, nrows = height)
- *   mask           optional uint8 (1 = exclude), src pixels; may be NULL
+ *   src            source geometry; the grid covers its row window [row0, row0+nrows) (the
+ *                  whole grid normally; a band of rows when the target is row-tiled across GPUs,
+ *                  cf. Scene._reduce_data, scene.py:930-954).  Source pixel indices and the
+ *                  mask / valid_input arrays are relative to the first pixel of that window.
+ *   mask           optional uint8 (1 = exclude), window pixels; may be NULL
  *   radius         radius_of_influence [m]
  *   valid_input    out, uint8 src pixels (NN_COORDINATES "valid_input_index")
  *   n_valid        out (host): number of valid source points

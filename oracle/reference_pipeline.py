@@ -10,12 +10,16 @@ from __future__ import annotations
 
 import os
 import time
+import warnings
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
 from . import calibration, nearest, solar
 from .projections import Area
+
+
+_ROW_EXTENT_CACHE: dict = {}
 
 
 def make_area(params) -> Area:
@@ -55,13 +59,17 @@ def abi_sunz_threaded(counts, band, src: Area, start_time, workers=None):
 
 
 def abi_sunz_nearest(counts, band, src_params, dst_params, start_time, radius, dst_rows: slice | None = None,
-                     workers=-1, timings: dict | None = None):
-    """The whole chain; ``dst_rows`` restricts the target to a row window (bounded CPU samples)."""
+                     src_rows: slice | None = None, workers=-1, timings: dict | None = None):
+    """The whole chain; ``dst_rows`` restricts the target to a row window and ``src_rows`` says which source rows
+    ``counts`` covers (bounded CPU samples: a target tile with the band of source rows that can reach it)."""
     src, dst = make_area(src_params), make_area(dst_params)
     t0 = time.perf_counter()
-    data = abi_sunz_threaded(counts, band, src, start_time)
+    if src_rows is None:
+        data = abi_sunz_threaded(counts, band, src, start_time)
+    else:
+        data = abi_sunz(counts, band, src, start_time, row_slice=src_rows)
     t1 = time.perf_counter()
-    slon, slat = src.get_lonlats()
+    slon, slat = src.get_lonlats(src_rows)
     dlon, dlat = dst.get_lonlats(dst_rows)
     t2 = time.perf_counter()
     valid_in, valid_out, index = nearest.get_neighbour_info(slon, slat, dlon, dlat, radius, workers=workers)
@@ -69,5 +77,32 @@ def abi_sunz_nearest(counts, band, src_params, dst_params, start_time, radius, d
     out = nearest.get_sample_from_neighbour_info(data, valid_in, index, np.float32(np.nan))
     t4 = time.perf_counter()
     if timings is not None:
-        timings.update(calibrate_sunz=t1 - t0, lonlats=t2 - t1, search=t3 - t2, gather=t4 - t3)
+        for k, v in (("calibrate_sunz", t1 - t0), ("lonlats", t2 - t1), ("search", t3 - t2), ("gather", t4 - t3)):
+            timings[k] = timings.get(k, 0.0) + v
     return out
+
+
+def source_rows_for_tile(src: Area, dst: Area, dst_rows: slice, radius, col_step=8, pad_rows=8) -> slice:
+    """Band of source rows that can hold neighbours of a target row tile (the CPU stand-in for
+    ``get_area_slices``, satpy/scene.py:942-947): latitude extents from every ``col_step``-th column."""
+    _, dlat = dst.proj.inverse(*np.meshgrid(dst.proj_vectors()[0][::max(1, dst.width // 512)],
+                                            dst.proj_vectors(rows=np.arange(dst.height)[dst_rows])[1]))
+    ok = np.isfinite(dlat)
+    if not ok.any():
+        return slice(0, 0)
+    margin = np.degrees(radius / nearest.R_EARTH) * 1.05 + 1e-6
+    lo, hi = dlat[ok].min() - margin, dlat[ok].max() + margin
+    key = (id(src), col_step)
+    if key not in _ROW_EXTENT_CACHE:
+        x, y = src.proj_vectors()
+        _, slat = src.proj.inverse(*np.meshgrid(x[::col_step], y))
+        with np.errstate(invalid="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            slat = np.where(np.isfinite(slat), slat, np.nan)
+            _ROW_EXTENT_CACHE[key] = (np.nanmin(slat, axis=1), np.nanmax(slat, axis=1))
+    rmin, rmax = _ROW_EXTENT_CACHE[key]
+    with np.errstate(invalid="ignore"):
+        hit = np.flatnonzero((rmax >= lo) & (rmin <= hi))
+    if hit.size == 0:
+        return slice(0, 0)
+    return slice(max(0, hit[0] - pad_rows), min(src.height, hit[-1] + 1 + pad_rows))

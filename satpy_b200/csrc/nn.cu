@@ -88,12 +88,12 @@ __global__ void __launch_bounds__(256)
 nn_count_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask, uint8_t *__restrict__ valid_input,
                 int32_t *__restrict__ counts, const int32_t *__restrict__ band_off, double inv_dphi, int nbands) {
     const int64_t W = S.g.width;
-    const int64_t n = S.g.height * W;
+    const int64_t n = S.g.nrows * W;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
         double lon, lat;
-        b200_geo_lonlat(S.g, r, i - r * W, lon, lat);
+        b200_geo_lonlat(S.g, S.g.row0 + r, i - r * W, lon, lat);
         bool ok = b200_lonlat_valid(lon, lat) && !(mask != nullptr && mask[i]);
         valid_input[i] = ok ? 1 : 0;
         if (ok) {
@@ -109,13 +109,13 @@ nn_scatter_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ 
                   int32_t *__restrict__ cursor, double4 *__restrict__ pts, const int32_t *__restrict__ band_off,
                   double inv_dphi, int nbands) {
     const int64_t W = S.g.width;
-    const int64_t n = S.g.height * W;
+    const int64_t n = S.g.nrows * W;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         if (!valid_input[i]) continue;
         int64_t r = i / W;
         double lon, lat;
-        b200_geo_lonlat(S.g, r, i - r * W, lon, lat);
+        b200_geo_lonlat(S.g, S.g.row0 + r, i - r * W, lon, lat);
         double x, y, z, lam, phi;
         b200_lonlat2xyz(lon, lat, x, y, z, lam, phi);
         int cell = b200_cell_of(band_off, lam, phi, inv_dphi, nbands);
@@ -173,8 +173,9 @@ extern "C" int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, d
     B200_CHECK_ARG(grid != nullptr && n_valid != nullptr, "NULL output argument");
     B200_CHECK_ARG(valid_input != nullptr, "valid_input is NULL");
     B200_CHECK_ARG(radius > 0.0 && isfinite(radius), "radius_of_influence must be positive and finite");
-    B200_CHECK_ARG(src->row0 == 0 && src->nrows == src->height, "the source geometry must cover the whole grid");
-    const int64_t n_src = src->height * src->width;
+    // the grid covers the source row window [row0, row0 + nrows); indices are relative to its first pixel
+    const int64_t n_src = src->nrows * src->width;
+    B200_CHECK_ARG(n_src > 0, "empty source row window");
     B200_CHECK_ARG(n_src < (1LL << 31), "more than 2^31 source pixels");
     cudaStream_t s = (cudaStream_t)stream;
 
@@ -217,7 +218,7 @@ extern "C" int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, d
     g->radius = radius;
     g->dphi = dphi;
     g->src_width = src->width;
-    g->src_height = src->height;
+    g->src_height = src->nrows;
     g->band_off = nullptr;
     g->cell_start = nullptr;
     g->pts = nullptr;

@@ -23,16 +23,21 @@ from .resample.nearest import _Grid
 class ABIResamplePipeline:
     """Reusable device state for resampling a stream of ABI images between two fixed geometries."""
 
-    def __init__(self, src_area, dst_area, radius_of_influence, row_window=None):
+    def __init__(self, src_area, dst_area, radius_of_influence, row_window=None, src_row_window=None):
+        """``row_window``: band of TARGET rows this instance produces; ``src_row_window``: band of SOURCE
+        rows it is fed (counts passed to ``run`` then cover only those rows) -- see satpy_b200.parallel."""
         self.torch = _lib.require_cuda()
         self.lib = _lib.load()
         self.src = as_geometry(src_area)
         self.dst = as_geometry(dst_area)
         self.radius = float(radius_of_influence)
         self.row0, self.nrows = (0, self.dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
+        self.src_row0, self.src_nrows = ((0, self.src.height) if src_row_window is None else
+                                         (int(src_row_window[0]), int(src_row_window[1])))
         torch = self.torch
-        self.refl = torch.empty(self.src.shape, dtype=torch.float32, device="cuda")
-        self.valid_input = torch.empty(self.src.shape, dtype=torch.uint8, device="cuda")
+        self.src_shape = (self.src_nrows, self.src.width)
+        self.refl = torch.empty(self.src_shape, dtype=torch.float32, device="cuda")
+        self.valid_input = torch.empty(self.src_shape, dtype=torch.uint8, device="cuda")
         self.grid = None
         self.gather_index = None
         self.n_valid = None
@@ -47,7 +52,7 @@ class ABIResamplePipeline:
         """counts (int16, device) -> sun-zenith-corrected reflectance [%] in ``self.refl``; one launch."""
         torch = self.torch
         s_cal = (_lib.AbiCalStruct * 1)(cal.struct("reflectance"))
-        g = self.src.geo_struct()
+        g = self.src.geo_struct(self.src_row0, self.src_nrows)
         sz = _sunz_struct(start_time, correction_limit, max_sza, True, 0)
         cptr = (C.c_void_p * 1)(counts_dev.data_ptr())
         optr = (C.c_void_p * 1)(self.refl.data_ptr())
@@ -61,7 +66,7 @@ class ABIResamplePipeline:
         self.grid = None
         n_valid = C.c_int64(0)
         handle = C.c_void_p(None)
-        gs = self.src.geo_struct()
+        gs = self.src.geo_struct(self.src_row0, self.src_nrows)
         _lib.check(self.lib.b200_nn_grid_create(C.byref(gs), None, self.radius, self.valid_input.data_ptr(),
                                                 C.byref(n_valid), C.byref(handle), _lib.stream_ptr(torch)))
         self.grid = _Grid(handle)
@@ -74,7 +79,7 @@ class ABIResamplePipeline:
         torch = self.torch
         gd = self.dst.geo_struct(self.row0, self.nrows)
         _lib.check(self.lib.b200_nn_query_gather_f32(self.grid.handle, C.byref(gd), self.radius, data.data_ptr(),
-                                                     out.data_ptr(), 1, self.src.size, out.numel(), fill,
+                                                     out.data_ptr(), 1, self.refl.numel(), out.numel(), fill,
                                                      _lib.stream_ptr(torch)))
         self.launches += 1
         return out
@@ -93,7 +98,7 @@ class ABIResamplePipeline:
         torch = self.torch
         fill_buf = (C.c_char * 4).from_buffer_copy(np.float32(fill).tobytes())
         _lib.check(self.lib.b200_nn_gather(data.data_ptr(), out.data_ptr(), self.gather_index.data_ptr(),
-                                           out.numel(), 1, self.src.size, out.numel(), 4,
+                                           out.numel(), 1, self.refl.numel(), out.numel(), 4,
                                            C.cast(fill_buf, C.c_void_p), _lib.stream_ptr(torch)))
         self.launches += 1
         return out
@@ -105,6 +110,13 @@ class ABIResamplePipeline:
         torch = self.torch
         if out is None:
             out = torch.empty(self.out_shape, dtype=torch.float32, device="cuda")
+        if self.nrows == 0:
+            return out
+        if self.src_nrows == 0:  # nothing of the source can reach this tile
+            out.fill_(float("nan"))
+            return out
+        if tuple(counts_dev.shape) != self.src_shape:
+            raise ValueError(f"counts shape {tuple(counts_dev.shape)} != source window shape {self.src_shape}")
         self.calibrate_sunz(counts_dev, cal, start_time)
         if reuse_neighbours:
             if self.gather_index is None:
@@ -115,6 +127,25 @@ class ABIResamplePipeline:
         self.build_grid()
         self.query_gather(self.refl, out)
         return out
+
+    def run_host(self, counts_host, cal, start_time, out_host, out_dev=None, reuse_neighbours=False):
+        """``run`` with HOST buffers (pinned torch tensors or numpy arrays): counts are copied to the device,
+        the image is copied back into ``out_host``; returns after the copy has completed."""
+        torch = self.torch
+        c = counts_host if isinstance(counts_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(counts_host))
+        o = out_host if isinstance(out_host, torch.Tensor) else torch.from_numpy(out_host)
+        if getattr(self, "_counts_dev", None) is None:
+            self._counts_dev = torch.empty(self.src_shape, dtype=torch.int16, device="cuda")
+        if c.numel():
+            self._counts_dev.copy_(c.view(torch.int16) if c.dtype == torch.uint16 else c, non_blocking=True)
+        out = self.run(self._counts_dev, cal, start_time, out=out_dev, reuse_neighbours=reuse_neighbours)
+        o.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+
+def _noop():  # pragma: no cover
+    pass
 
 
 def abi_sunz_nearest(counts, cal, src_area, dst_area, start_time, radius_of_influence, row_window=None):
