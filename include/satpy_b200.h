@@ -161,6 +161,14 @@ typedef struct b200_nn_grid b200_nn_grid_t; /* opaque, owned by the library */
 int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, double radius,
                         uint8_t *valid_input, int64_t *n_valid /* host */,
                         b200_nn_grid_t **grid /* host out */, void *stream);
+/* Same, choosing the search engine: 0 = automatic, 1 = bucket grid (any source), 2 = fixed grid
+ * (geostationary area sources only: the source lattice itself is the index, see csrc/nn_geos.cu;
+ * B200_EUNSUPPORTED for other sources).  Both engines return identical indices. */
+int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask, double radius,
+                           uint8_t *valid_input, int64_t *n_valid /* host */,
+                           b200_nn_grid_t **grid /* host out */, int32_t method, void *stream);
+/* engine actually used by a grid (1 or 2) */
+int b200_nn_grid_method(const b200_nn_grid_t *grid, int32_t *method /* host */);
 int b200_nn_grid_destroy(b200_nn_grid_t *grid);
 /* bytes of device memory held by the grid */
 int b200_nn_grid_nbytes(const b200_nn_grid_t *grid, int64_t *nbytes /* host */);

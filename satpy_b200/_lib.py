@@ -71,6 +71,8 @@ SIGNATURES = {
     "b200_abi_vis_sunz": (C.c_int, [C.POINTER(_P), C.POINTER(_P), C.POINTER(AbiCalStruct), C.c_int32, _GEO,
                                     C.POINTER(SunzStruct), _P]),
     "b200_nn_grid_create": (C.c_int, [_GEO, _P, C.c_double, _P, C.POINTER(C.c_int64), C.POINTER(_P), _P]),
+    "b200_nn_grid_create_ex": (C.c_int, [_GEO, _P, C.c_double, _P, C.POINTER(C.c_int64), C.POINTER(_P), C.c_int32, _P]),
+    "b200_nn_grid_method": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "b200_nn_grid_destroy": (C.c_int, [_P]),
     "b200_nn_grid_nbytes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "b200_nn_query": (C.c_int, [_P, _GEO, C.c_double, _P, _P, _P, _P]),

@@ -53,7 +53,10 @@ __device__ __forceinline__ double b200_authlat(double beta, const double *apa) {
 
 // Inverse projection: projected metres -> lon/lat degrees.  Returns false (and +inf) when the
 // point has no inverse (e.g. off the geostationary disk).
-__device__ __forceinline__ bool b200_proj_inverse(const b200_proj_t &P, double x, double y,
+// NOT inlined on purpose: nvcc contracts a*b+c into FMAs differently depending on the surrounding code, and
+// a last-ulp difference in lon/lat between two kernels would let them break exact distance ties differently.
+// One out-of-line body per translation unit keeps every kernel's coordinates bit-identical.
+static __device__ __noinline__ bool b200_proj_inverse(const b200_proj_t &P, double x, double y,
                                                   double &lon, double &lat) {
     if (P.kind == B200_PROJ_LONGLAT) {
         lon = x;
@@ -224,7 +227,7 @@ __device__ __forceinline__ bool b200_proj_inverse(const b200_proj_t &P, double x
 }
 
 // Forward projection: lon/lat degrees -> projected metres.  false (+inf) when not projectable.
-__device__ __forceinline__ bool b200_proj_forward(const b200_proj_t &P, double lon, double lat,
+static __device__ __noinline__ bool b200_proj_forward(const b200_proj_t &P, double lon, double lat,
                                                   double &x, double &y) {
     if (P.kind == B200_PROJ_LONGLAT) {
         x = lon;

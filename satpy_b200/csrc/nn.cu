@@ -1,4 +1,4 @@
-// Nearest-neighbour resampling on sm_100a: bucket-grid search + gather.
+// Nearest-neighbour resampling on sm_100a: search-structure life cycle, the bucket-grid engine, the gather.
 //
 // Replaces
 //   pyresample.kd_tree.XArrayResamplerNN.get_neighbour_info   (pykdtree build + query; reached from
@@ -10,36 +10,21 @@
 // distance is < radius_of_influence, misses are -1, and index_array indexes the compressed
 // valid-input vector.
 //
-// The kd-tree is replaced by a uniform bucket grid on the sphere: latitude bands of height >= the
-// search cap angle, each band cut into ~square longitude cells; cells of a band are contiguous, and
-// the valid source points are counting-sorted by cell into one array of 32-byte records
-// {x, y, z, raw index}.  A query turns the spherical cap of the search radius into (bands) x (one or
-// two contiguous cell ranges per band), i.e. a handful of contiguous record ranges that it scans
-// with 128-bit loads.  Ties (exactly equal float64 distance) go to the lowest source index, so the
-// result does not depend on the (atomic, unordered) placement inside a cell.
+// Two exact engines stand in for the kd-tree; both break exact float64 distance ties towards the lowest
+// source index, so they return identical indices:
+//   * bucket grid (this file; any source, swath or area): latitude bands of height >= the search cap
+//     angle, each band cut into ~square longitude cells; cells of a band are contiguous, and the valid
+//     source points are counting-sorted by cell into one array of 32-byte records {x, y, z, raw index}.
+//     A query turns the spherical cap of the search radius into (bands) x (one or two contiguous cell
+//     ranges per band), i.e. a handful of contiguous record ranges that it scans with 128-bit loads.
+//   * fixed grid (nn_geos.cu; geostationary area sources): the source grid itself is the index.
+// Targets whose lon depends on the column only and lat on the row only (longlat / eqc / merc) get
+// per-column and per-row tables so that no transcendental is evaluated per pixel.
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
-#include "b200_common.cuh"
-#include "b200_proj.cuh"
+#include "nn_common.cuh"
 
-int b200_check_geo(const b200_geo_t *geo, const char *who);
-
-#define B200_R_EARTH 6370997.0
-#define B200_TWO_PI 6.283185307179586476925287
 #define B200_NN_MAX_CELLS (160LL * 1000 * 1000)
-
-struct b200_nn_grid {
-    int64_t n_src, n_valid, ncells;
-    int64_t src_width, src_height;
-    int32_t nbands;
-    double radius, dphi;
-    int32_t *band_off;    // [nbands + 1] first cell of each band
-    int32_t *cell_start;  // [ncells + 1] first record of each cell
-    double4 *pts;         // [n_valid] {x, y, z, raw source index (bit pattern)} sorted by cell
-    int32_t *prefix;      // [n_src] exclusive prefix sum of valid_input: raw -> compressed index
-    int64_t nbytes;
-    int device;
-};
 
 struct GridDev {
     const int32_t *band_off;
@@ -53,19 +38,6 @@ struct GridDev {
 struct SrcArg {
     b200_geo_t g;
 };
-
-// lon/lat (degrees) -> spherical cartesian, pyresample's R (kd_tree / geometry module constant)
-__device__ __forceinline__ void b200_lonlat2xyz(double lon, double lat, double &x, double &y, double &z,
-                                                double &lam, double &phi) {
-    lam = lon * B200_DEG2RAD;
-    phi = lat * B200_DEG2RAD;
-    double sl, cl, sp, cp;
-    sincos(lam, &sl, &cl);
-    sincos(phi, &sp, &cp);
-    x = B200_R_EARTH * cp * cl;
-    y = B200_R_EARTH * cp * sl;
-    z = B200_R_EARTH * sp;
-}
 
 __device__ __forceinline__ int b200_band_of(double phi, double inv_dphi, int nbands) {
     int b = (int)floor((phi + B200_HALFPI) * inv_dphi);
@@ -83,10 +55,12 @@ __device__ __forceinline__ int b200_cell_of(const int32_t *__restrict__ band_off
 }
 
 // ---------------------------------------------------------------------------------------- build
-// pass 1: validity + per-cell histogram
+// ONE pass over the source for both engines: validity, the record {x, y, z, raw index} by raw index (x = NaN marks an
+// invalid pixel) and, for the bucket engine, the cell of every valid point.
 __global__ void __launch_bounds__(256)
-nn_count_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask, uint8_t *__restrict__ valid_input,
-                int32_t *__restrict__ counts, const int32_t *__restrict__ band_off, double inv_dphi, int nbands) {
+nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask,
+                        uint8_t *__restrict__ valid_input, double4 *__restrict__ rec, int32_t *__restrict__ cell_of,
+                        const int32_t *__restrict__ band_off, double inv_dphi, int nbands) {
     const int64_t W = S.g.width;
     const int64_t n = S.g.nrows * W;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -96,31 +70,37 @@ nn_count_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ ma
         b200_geo_lonlat(S.g, S.g.row0 + r, i - r * W, lon, lat);
         bool ok = b200_lonlat_valid(lon, lat) && !(mask != nullptr && mask[i]);
         valid_input[i] = ok ? 1 : 0;
-        if (ok) {
-            int cell = b200_cell_of(band_off, lon * B200_DEG2RAD, lat * B200_DEG2RAD, inv_dphi, nbands);
-            atomicAdd(counts + cell, 1);
-        }
+        double x = __longlong_as_double(0x7ff8000000000000LL), y = 0.0, z = 0.0, lam = 0.0, phi = 0.0;
+        if (ok) b200_lonlat2xyz(lon, lat, x, y, z, lam, phi);
+        double2 *p = reinterpret_cast<double2 *>(rec + i);
+        p[0] = make_double2(x, y);
+        p[1] = make_double2(z, __longlong_as_double((long long)i));
+        if (cell_of) cell_of[i] = ok ? b200_cell_of(band_off, lam, phi, inv_dphi, nbands) : -1;
     }
 }
 
-// pass 2: scatter the records into their cells
 __global__ void __launch_bounds__(256)
-nn_scatter_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ valid_input,
-                  int32_t *__restrict__ cursor, double4 *__restrict__ pts, const int32_t *__restrict__ band_off,
-                  double inv_dphi, int nbands) {
-    const int64_t W = S.g.width;
-    const int64_t n = S.g.nrows * W;
+nn_cell_count_kernel(const int32_t *__restrict__ cell_of, int64_t n, int32_t *__restrict__ counts) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        if (!valid_input[i]) continue;
-        int64_t r = i / W;
-        double lon, lat;
-        b200_geo_lonlat(S.g, S.g.row0 + r, i - r * W, lon, lat);
-        double x, y, z, lam, phi;
-        b200_lonlat2xyz(lon, lat, x, y, z, lam, phi);
-        int cell = b200_cell_of(band_off, lam, phi, inv_dphi, nbands);
-        int slot = atomicAdd(cursor + cell, 1);
-        pts[slot] = make_double4(x, y, z, __longlong_as_double((long long)i));
+        int c = cell_of[i];
+        if (c >= 0) atomicAdd(counts + c, 1);
+    }
+}
+
+// counting sort, second half: move the records into their cells
+__global__ void __launch_bounds__(256)
+nn_cell_scatter_kernel(const int32_t *__restrict__ cell_of, const double4 *__restrict__ rec, int64_t n,
+                       int32_t *__restrict__ cursor, double4 *__restrict__ pts) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int c = cell_of[i];
+        if (c < 0) continue;
+        int slot = atomicAdd(cursor + c, 1);
+        const double2 *q = reinterpret_cast<const double2 *>(rec + i);
+        double2 *p = reinterpret_cast<double2 *>(pts + slot);
+        p[0] = q[0];
+        p[1] = q[1];
     }
 }
 
@@ -128,10 +108,19 @@ struct U8ToI32 {
     __host__ __device__ __forceinline__ int32_t operator()(const uint8_t &v) const { return (int32_t)v; }
 };
 
-static double cap_angle(double radius) {
-    double h = radius / (2.0 * B200_R_EARTH);
-    if (h >= 1.0) return B200_PI;
-    return 2.0 * asin(h) * (1.0 + 1e-9) + 1e-12;
+// Device memory of a search structure comes from the stream-ordered pool: after the first build, rebuilding for the
+// next scene allocates without a device synchronisation.  All uses of a structure must be on the stream it was
+// created on (the caller's current stream).
+static void nn_pool_keep_memory() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
 }
 
 extern "C" int b200_nn_grid_destroy(b200_nn_grid_t *grid) {
@@ -139,10 +128,11 @@ extern "C" int b200_nn_grid_destroy(b200_nn_grid_t *grid) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(grid->device);
-    cudaFree(grid->band_off);
-    cudaFree(grid->cell_start);
-    cudaFree(grid->pts);
-    cudaFree(grid->prefix);
+    cudaStream_t s = (cudaStream_t)grid->stream;
+    if (grid->band_off) cudaFreeAsync(grid->band_off, s);
+    if (grid->cell_start) cudaFreeAsync(grid->cell_start, s);
+    if (grid->pts) cudaFreeAsync(grid->pts, s);
+    if (grid->prefix) cudaFreeAsync(grid->prefix, s);
     cudaSetDevice(prev);
     delete grid;
     return B200_OK;
@@ -154,165 +144,193 @@ extern "C" int b200_nn_grid_nbytes(const b200_nn_grid_t *grid, int64_t *nbytes) 
     return B200_OK;
 }
 
-#define NN_CUDA_OR_FREE(call)                                                                       \
-    do {                                                                                            \
-        cudaError_t err__ = (call);                                                                 \
-        if (err__ != cudaSuccess) {                                                                 \
-            b200_set_error("b200_nn_grid_create: %s failed: %s", #call, cudaGetErrorString(err__)); \
-            cudaFree(counts);                                                                       \
-            cudaFree(tmp);                                                                          \
-            b200_nn_grid_destroy(g);                                                                \
-            return err__ == cudaErrorMemoryAllocation ? B200_ENOMEM : B200_ECUDA;                   \
-        }                                                                                           \
+#define NN_TRY(call)                                                                        \
+    do {                                                                                    \
+        cudaError_t err__ = (call);                                                         \
+        if (err__ != cudaSuccess) {                                                         \
+            b200_set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(err__)); \
+            rc = err__ == cudaErrorMemoryAllocation ? B200_ENOMEM : B200_ECUDA;             \
+            goto fail;                                                                      \
+        }                                                                                   \
     } while (0)
 
-extern "C" int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, double radius, uint8_t *valid_input,
-                                   int64_t *n_valid, b200_nn_grid_t **grid, void *stream) {
+// exclusive prefix sum of the valid mask (raw -> compressed index) and the number of valid points
+static int nn_prefix(b200_nn_grid *g, const uint8_t *valid_input, cudaStream_t s) {
+    int rc = B200_OK;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int32_t last_prefix = 0;
+    uint8_t last_valid = 0;
+    thrust::transform_iterator<U8ToI32, const uint8_t *> vit(valid_input, U8ToI32());
+    NN_TRY(cudaMallocAsync((void **)&g->prefix, (size_t)g->n_src * sizeof(int32_t), s));
+    NN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, vit, g->prefix, (int)g->n_src, s));
+    NN_TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+    NN_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, vit, g->prefix, (int)g->n_src, s));
+    NN_TRY(cudaMemcpyAsync(&last_prefix, g->prefix + g->n_src - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    NN_TRY(cudaMemcpyAsync(&last_valid, valid_input + g->n_src - 1, 1, cudaMemcpyDeviceToHost, s));
+    NN_TRY(cudaStreamSynchronize(s));
+    g->n_valid = (int64_t)last_prefix + (last_valid ? 1 : 0);
+fail:
+    if (tmp) cudaFreeAsync(tmp, s);
+    return rc;
+}
+
+static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask, uint8_t *valid_input,
+                    cudaStream_t s) {
+    int rc = B200_OK;
+    const bool bucket = g->mode == B200_NN_BUCKET;
+    const int64_t n_src = g->n_src;
+    int32_t *counts = nullptr, *cell_of = nullptr, *h_off = nullptr;
+    double4 *rec = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int64_t ncells = 0;
+    int nbands = 1;
+    double inv_dphi = 1.0;
+    SrcArg S;
+    S.g = *src;
+    nn_pool_keep_memory();
+    if (bucket) {
+        // ---- host: band layout.  Band height >= cap angle; widened if the table would get too large.
+        double dphi = b200_cap_angle(g->radius);
+        double min_dphi = sqrt(4.0 * B200_PI / (double)B200_NN_MAX_CELLS);
+        if (dphi < min_dphi) dphi = min_dphi;
+        if (dphi > B200_PI) dphi = B200_PI;
+        nbands = (int)ceil(B200_PI / dphi);
+        if (nbands < 1) nbands = 1;
+        inv_dphi = 1.0 / dphi;
+        h_off = new (std::nothrow) int32_t[nbands + 1];
+        if (!h_off) {
+            b200_set_error("b200_nn_grid_create: out of host memory");
+            return B200_ENOMEM;
+        }
+        for (int b = 0; b < nbands; ++b) {
+            double lo = -B200_HALFPI + b * dphi, hi = lo + dphi;
+            if (hi > B200_HALFPI) hi = B200_HALFPI;
+            double cmax = (lo <= 0.0 && hi >= 0.0) ? 1.0 : fmax(cos(lo), cos(hi));
+            int64_t nb = (int64_t)floor(B200_TWO_PI * cmax / dphi);
+            if (nb < 1) nb = 1;
+            h_off[b] = (int32_t)ncells;
+            ncells += nb;
+        }
+        h_off[nbands] = (int32_t)ncells;
+        g->ncells = ncells;
+        g->nbands = nbands;
+        g->dphi = dphi;
+        NN_TRY(cudaMallocAsync((void **)&g->band_off, (size_t)(nbands + 1) * sizeof(int32_t), s));
+        NN_TRY(cudaMemcpyAsync(g->band_off, h_off, (size_t)(nbands + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        NN_TRY(cudaStreamSynchronize(s));  // h_off is pageable: finish before freeing it
+        NN_TRY(cudaMallocAsync((void **)&cell_of, (size_t)n_src * sizeof(int32_t), s));
+    }
+    NN_TRY(cudaMallocAsync((void **)&rec, (size_t)n_src * sizeof(double4), s));
+    nn_source_points_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, mask, valid_input, rec, cell_of,
+                                                                        g->band_off, inv_dphi, nbands);
+    NN_TRY(cudaGetLastError());
+    rc = nn_prefix(g, valid_input, s);
+    if (rc) goto fail;
+    if (!bucket) {
+        g->pts = rec;  // the raw-indexed records ARE the search structure
+        rec = nullptr;
+        g->nbytes = n_src * (int64_t)(sizeof(double4) + sizeof(int32_t));
+        goto fail;  // (common clean-up)
+    }
+    NN_TRY(cudaMallocAsync((void **)&g->cell_start, (size_t)(ncells + 1) * sizeof(int32_t), s));
+    NN_TRY(cudaMallocAsync((void **)&counts, (size_t)(ncells + 1) * sizeof(int32_t), s));
+    NN_TRY(cudaMemsetAsync(counts, 0, (size_t)(ncells + 1) * sizeof(int32_t), s));
+    nn_cell_count_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(cell_of, n_src, counts);
+    NN_TRY(cudaGetLastError());
+    NN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, g->cell_start, (int)(ncells + 1), s));
+    NN_TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+    NN_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, g->cell_start, (int)(ncells + 1), s));
+    // counts becomes the per-cell write cursor
+    NN_TRY(cudaMemcpyAsync(counts, g->cell_start, (size_t)ncells * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    NN_TRY(cudaMallocAsync((void **)&g->pts, (size_t)(g->n_valid > 0 ? g->n_valid : 1) * sizeof(double4), s));
+    if (g->n_valid > 0) {
+        nn_cell_scatter_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(cell_of, rec, n_src, counts, g->pts);
+        NN_TRY(cudaGetLastError());
+    }
+    g->nbytes = (int64_t)(nbands + 1) * 4 + (ncells + 1) * 4 + n_src * 4 + (g->n_valid > 0 ? g->n_valid : 1) * 32;
+fail:
+    delete[] h_off;
+    if (counts) cudaFreeAsync(counts, s);
+    if (cell_of) cudaFreeAsync(cell_of, s);
+    if (rec) cudaFreeAsync(rec, s);
+    if (tmp) cudaFreeAsync(tmp, s);
+    return rc;
+}
+
+extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask, double radius, uint8_t *valid_input,
+                                      int64_t *n_valid, b200_nn_grid_t **grid, int32_t method, void *stream) {
     int rc = b200_check_geo(src, "b200_nn_grid_create");
     if (rc) return rc;
     B200_CHECK_ARG(grid != nullptr && n_valid != nullptr, "NULL output argument");
     B200_CHECK_ARG(valid_input != nullptr, "valid_input is NULL");
     B200_CHECK_ARG(radius > 0.0 && isfinite(radius), "radius_of_influence must be positive and finite");
-    // the grid covers the source row window [row0, row0 + nrows); indices are relative to its first pixel
+    B200_CHECK_ARG(method >= 0 && method <= 2, "method must be 0 (auto), 1 (bucket grid) or 2 (fixed grid)");
+    // the structure covers the source row window [row0, row0 + nrows); indices are relative to its first pixel
     const int64_t n_src = src->nrows * src->width;
     B200_CHECK_ARG(n_src > 0, "empty source row window");
     B200_CHECK_ARG(n_src < (1LL << 31), "more than 2^31 source pixels");
-    cudaStream_t s = (cudaStream_t)stream;
-
-    // ---- host: band layout.  Band height >= cap angle; widened if the table would get too large.
-    double theta = cap_angle(radius);
-    double dphi = theta;
-    double min_dphi = sqrt(4.0 * B200_PI / (double)B200_NN_MAX_CELLS);
-    if (dphi < min_dphi) dphi = min_dphi;
-    if (dphi > B200_PI) dphi = B200_PI;
-    int nbands = (int)ceil(B200_PI / dphi);
-    if (nbands < 1) nbands = 1;
-    int32_t *h_off = new (std::nothrow) int32_t[nbands + 1];
-    if (!h_off) {
-        b200_set_error("b200_nn_grid_create: out of host memory");
-        return B200_ENOMEM;
+    const bool fixed_ok = b200_nn_fixed_grid_supported(src) != 0;
+    if (method == B200_NN_FIXED_GRID && !fixed_ok) {
+        b200_set_error("b200_nn_grid_create: the fixed-grid search needs a geostationary area source");
+        return B200_EUNSUPPORTED;
     }
-    int64_t ncells = 0;
-    for (int b = 0; b < nbands; ++b) {
-        double lo = -B200_HALFPI + b * dphi, hi = lo + dphi;
-        if (hi > B200_HALFPI) hi = B200_HALFPI;
-        double cmax = (lo <= 0.0 && hi >= 0.0) ? 1.0 : fmax(cos(lo), cos(hi));
-        int64_t nb = (int64_t)floor(B200_TWO_PI * cmax / dphi);
-        if (nb < 1) nb = 1;
-        h_off[b] = (int32_t)ncells;
-        ncells += nb;
-    }
-    h_off[nbands] = (int32_t)ncells;
-
     b200_nn_grid *g = new (std::nothrow) b200_nn_grid();
-    int32_t *counts = nullptr;
-    void *tmp = nullptr;
     if (!g) {
-        delete[] h_off;
         b200_set_error("b200_nn_grid_create: out of host memory");
         return B200_ENOMEM;
     }
+    memset(g, 0, sizeof(*g));
+    g->mode = (method == 0) ? (fixed_ok ? B200_NN_FIXED_GRID : B200_NN_BUCKET) : method;
     g->n_src = n_src;
-    g->ncells = ncells;
-    g->nbands = nbands;
     g->radius = radius;
-    g->dphi = dphi;
-    g->src_width = src->width;
-    g->src_height = src->nrows;
-    g->band_off = nullptr;
-    g->cell_start = nullptr;
-    g->pts = nullptr;
-    g->prefix = nullptr;
+    g->src = *src;
     cudaGetDevice(&g->device);
-    const double inv_dphi = 1.0 / dphi;
-
-    cudaError_t e0 = cudaMalloc(&g->band_off, (size_t)(nbands + 1) * sizeof(int32_t));
-    if (e0 == cudaSuccess)
-        e0 = cudaMemcpyAsync(g->band_off, h_off, (size_t)(nbands + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s);
-    if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(s);  // h_off is pageable: finish before freeing it
-    delete[] h_off;
-    NN_CUDA_OR_FREE(e0);
-    NN_CUDA_OR_FREE(cudaMalloc(&g->cell_start, (size_t)(ncells + 1) * sizeof(int32_t)));
-    NN_CUDA_OR_FREE(cudaMalloc(&g->prefix, (size_t)n_src * sizeof(int32_t)));
-    NN_CUDA_OR_FREE(cudaMalloc(&counts, (size_t)(ncells + 1) * sizeof(int32_t)));
-    NN_CUDA_OR_FREE(cudaMemsetAsync(counts, 0, (size_t)(ncells + 1) * sizeof(int32_t), s));
-
-    SrcArg S;
-    S.g = *src;
-    nn_count_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, mask, valid_input, counts, g->band_off,
-                                                                inv_dphi, nbands);
-    NN_CUDA_OR_FREE(cudaGetLastError());
-
-    // exclusive scans: cell histogram -> cell_start, valid mask -> compressed index
-    size_t tmp_a = 0, tmp_b = 0;
-    thrust::transform_iterator<U8ToI32, const uint8_t *> vit(valid_input, U8ToI32());
-    NN_CUDA_OR_FREE(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, counts, g->cell_start, (int)(ncells + 1), s));
-    NN_CUDA_OR_FREE(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, vit, g->prefix, (int)n_src, s));
-    size_t tmp_bytes = tmp_a > tmp_b ? tmp_a : tmp_b;
-    NN_CUDA_OR_FREE(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
-    NN_CUDA_OR_FREE(cub::DeviceScan::ExclusiveSum(tmp, tmp_a, counts, g->cell_start, (int)(ncells + 1), s));
-    NN_CUDA_OR_FREE(cub::DeviceScan::ExclusiveSum(tmp, tmp_b, vit, g->prefix, (int)n_src, s));
-    int32_t total = 0;
-    NN_CUDA_OR_FREE(cudaMemcpyAsync(&total, g->cell_start + ncells, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    NN_CUDA_OR_FREE(cudaStreamSynchronize(s));
-    g->n_valid = total;
-
-    // counts becomes the per-cell write cursor
-    NN_CUDA_OR_FREE(cudaMemcpyAsync(counts, g->cell_start, (size_t)ncells * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
-    NN_CUDA_OR_FREE(cudaMalloc(&g->pts, (size_t)(total > 0 ? total : 1) * sizeof(double4)));
-    if (total > 0) {
-        nn_scatter_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, valid_input, counts, g->pts, g->band_off,
-                                                                      inv_dphi, nbands);
-        NN_CUDA_OR_FREE(cudaGetLastError());
+    cudaStream_t s = (cudaStream_t)stream;
+    g->stream = stream;
+    rc = nn_build(g, src, mask, valid_input, s);
+    if (rc) {
+        b200_nn_grid_destroy(g);
+        return rc;
     }
-    NN_CUDA_OR_FREE(cudaStreamSynchronize(s));
-    cudaFree(counts);
-    cudaFree(tmp);
-    g->nbytes = (int64_t)(nbands + 1) * 4 + (ncells + 1) * 4 + n_src * 4 + (int64_t)(total > 0 ? total : 1) * 32;
-    *n_valid = total;
+    *n_valid = g->n_valid;
     *grid = g;
     return B200_OK;
 }
 
-// ---------------------------------------------------------------------------------------- query
-struct Best {
-    double d2;
-    long long idx;
-};
-
-__device__ __forceinline__ void nn_scan_range(const double4 *__restrict__ pts, int s, int e, double tx, double ty,
-                                              double tz, Best &best) {
-    for (int j = s; j < e; ++j) {
-        const double2 *p = reinterpret_cast<const double2 *>(pts + j);
-        double2 a = __ldg(p);
-        double2 b = __ldg(p + 1);
-        double dx = a.x - tx, dy = a.y - ty, dz = b.x - tz;
-        double d2 = dx * dx + dy * dy + dz * dz;
-        long long idx = __double_as_longlong(b.y);
-        if (d2 < best.d2 || (d2 == best.d2 && idx < best.idx)) {
-            best.d2 = d2;
-            best.idx = idx;
-        }
-    }
+extern "C" int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, double radius, uint8_t *valid_input,
+                                   int64_t *n_valid, b200_nn_grid_t **grid, void *stream) {
+    return b200_nn_grid_create_ex(src, mask, radius, valid_input, n_valid, grid, 0, stream);
 }
 
-// nearest valid source point of one target lon/lat (degrees); -1 when none within the radius
-__device__ __forceinline__ long long nn_query_point(const GridDev &G, double lon, double lat, double theta,
-                                                    double sin_theta, double r2) {
-    double tx, ty, tz, lam, phi;
-    b200_lonlat2xyz(lon, lat, tx, ty, tz, lam, phi);
+extern "C" int b200_nn_grid_method(const b200_nn_grid_t *grid, int32_t *method) {
+    B200_CHECK_ARG(grid != nullptr && method != nullptr, "NULL argument");
+    *method = grid->mode;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------- query
+__device__ __forceinline__ void nn_scan_range(const double4 *__restrict__ pts, int s, int e, double tx, double ty,
+                                              double tz, Best &best) {
+    for (int j = s; j < e; ++j) b200_nn_consider(pts + j, tx, ty, tz, best);
+}
+
+// longitude half-width of the spherical cap of angular radius theta centred at latitude phi (>= pi: all longitudes)
+__device__ __forceinline__ double nn_cap_dlam(double phi, double theta, double sin_theta) {
+    if (fabs(phi) + theta >= B200_HALFPI - 1e-12) return 4.0;
+    double q = sin_theta / cos(phi);
+    if (q >= 1.0) return 4.0;
+    return asin(q) * (1.0 + 1e-12) + 1e-12;
+}
+
+// nearest valid source point of one target given its spherical coordinates; -1 when none within the radius
+__device__ __forceinline__ long long nn_bucket_point(const GridDev &G, double lam, double tx, double ty, double tz,
+                                                     int b_lo, int b_hi, double dlam, double r2) {
     Best best;
     best.d2 = r2;  // strict "<": a neighbour exactly at the radius is not accepted
     best.idx = -1;
-    int b_lo = b200_band_of(phi - theta, G.inv_dphi, G.nbands);
-    int b_hi = b200_band_of(phi + theta, G.inv_dphi, G.nbands);
-    bool full = (fabs(phi) + theta >= B200_HALFPI - 1e-12);
-    double dlam = B200_PI;
-    if (!full) {
-        double q = sin_theta / cos(phi);
-        dlam = (q >= 1.0) ? B200_PI : asin(q) * (1.0 + 1e-12) + 1e-12;
-        if (q >= 1.0) full = true;
-    }
+    const bool full = dlam >= B200_PI;
     for (int b = b_lo; b <= b_hi; ++b) {
         int off = __ldg(G.band_off + b);
         int nb = __ldg(G.band_off + b + 1) - off;
@@ -339,12 +357,14 @@ __device__ __forceinline__ long long nn_query_point(const GridDev &G, double lon
 struct QueryArg {
     b200_geo_t dst;
     GridDev G;
+    QueryOut O;
     double theta, sin_theta, r2;
+    const TgtCol *cols;  // rectilinear targets only
+    const TgtRow *rows;
 };
 
-__global__ void __launch_bounds__(256)
-nn_query_kernel(const __grid_constant__ QueryArg Q, int32_t *__restrict__ index_array,
-                int32_t *__restrict__ gather_index, uint8_t *__restrict__ valid_output) {
+// general targets: everything per pixel
+__global__ void __launch_bounds__(256) nn_bucket_query_kernel(const __grid_constant__ QueryArg Q) {
     const int64_t W = Q.dst.width;
     const int64_t n = Q.dst.nrows * W;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -353,33 +373,166 @@ nn_query_kernel(const __grid_constant__ QueryArg Q, int32_t *__restrict__ index_
         double lon, lat;
         b200_geo_lonlat(Q.dst, Q.dst.row0 + r, i - r * W, lon, lat);
         bool ok = b200_lonlat_valid(lon, lat);
-        long long raw = ok ? nn_query_point(Q.G, lon, lat, Q.theta, Q.sin_theta, Q.r2) : -1;
-        if (valid_output) valid_output[i] = ok ? 1 : 0;
-        if (gather_index) gather_index[i] = (int32_t)raw;
-        if (index_array) index_array[i] = raw < 0 ? -1 : __ldg(Q.G.prefix + raw);
+        long long raw = -1;
+        if (ok) {
+            double tx, ty, tz, lam, phi;
+            b200_lonlat2xyz(lon, lat, tx, ty, tz, lam, phi);
+            int b_lo = b200_band_of(phi - Q.theta, Q.G.inv_dphi, Q.G.nbands);
+            int b_hi = b200_band_of(phi + Q.theta, Q.G.inv_dphi, Q.G.nbands);
+            raw = nn_bucket_point(Q.G, lam, tx, ty, tz, b_lo, b_hi, nn_cap_dlam(phi, Q.theta, Q.sin_theta), Q.r2);
+        }
+        b200_nn_emit(Q.O, Q.G.prefix, i, raw, ok);
     }
 }
 
+// rectilinear targets: one block iteration = 256 consecutive columns of one row, tables instead of trigonometry
+__global__ void __launch_bounds__(256) nn_bucket_query_rect_kernel(const __grid_constant__ QueryArg Q) {
+    const int W = (int)Q.dst.width;
+    const int nseg = (W + 255) >> 8;
+    const int64_t items = (int64_t)Q.dst.nrows * nseg;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        int r = (int)(it / nseg);
+        int col = (int)(it - (int64_t)r * nseg) * 256 + threadIdx.x;
+        if (col >= W) continue;
+        const TgtRow R = Q.rows[r];
+        const TgtCol Cc = Q.cols[col];
+        bool ok = R.valid && Cc.valid;
+        long long raw = -1;
+        if (ok) {
+            double tx = B200_R_EARTH * R.cos_phi * Cc.cos_lam;
+            double ty = B200_R_EARTH * R.cos_phi * Cc.sin_lam;
+            double tz = B200_R_EARTH * R.sin_phi;
+            raw = nn_bucket_point(Q.G, Cc.lam, tx, ty, tz, R.b_lo, R.b_hi, R.dlam, Q.r2);
+        }
+        b200_nn_emit(Q.O, Q.G.prefix, (int64_t)r * W + col, raw, ok);
+    }
+}
+
+// Tables of a rectilinear target (lon from the column, lat from the row), bit-identical to the per-pixel path.
+struct TableArg {
+    b200_geo_t dst;
+    double theta, sin_theta, inv_dphi;  // bucket mode
+    int32_t nbands, geos;
+    double lam0;                        // fixed-grid mode: geos source constants
+    double rp, rp2;
+};
+
 __global__ void __launch_bounds__(256)
-nn_query_gather_f32_kernel(const __grid_constant__ QueryArg Q, const float *__restrict__ data,
-                           float *__restrict__ out, int nbands, int64_t src_band_stride, int64_t dst_band_stride,
-                           float fill) {
-    const int64_t W = Q.dst.width;
-    const int64_t n = Q.dst.nrows * W;
+nn_target_tables_kernel(const __grid_constant__ TableArg A, TgtCol *__restrict__ cols, TgtRow *__restrict__ rows) {
+    const int64_t W = A.dst.width, H = A.dst.nrows;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int64_t r = i / W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < W + H; i += stride) {
         double lon, lat;
-        b200_geo_lonlat(Q.dst, Q.dst.row0 + r, i - r * W, lon, lat);
-        long long raw = b200_lonlat_valid(lon, lat) ? nn_query_point(Q.G, lon, lat, Q.theta, Q.sin_theta, Q.r2) : -1;
-        for (int b = 0; b < nbands; ++b) {
-            float v = raw < 0 ? fill : __ldg(data + b * src_band_stride + raw);
-            st_stream_f1(out + b * dst_band_stride + i, v);
+        if (i < W) {
+            b200_geo_lonlat(A.dst, A.dst.row0, i, lon, lat);
+            TgtCol c;
+            c.lam = lon * B200_DEG2RAD;
+            sincos(c.lam, &c.sin_lam, &c.cos_lam);
+            c.valid = (lon >= -180.0 && lon <= 180.0) ? 1 : 0;
+            double rel = b200_adjlon(c.lam - A.lam0);
+            c.s_rel = (float)sin(rel);
+            c.c_rel = (float)cos(rel);
+            c.pad = 0;
+            c.pad2 = 0.0;
+            cols[i] = c;
+        } else {
+            int64_t r = i - W;
+            b200_geo_lonlat(A.dst, A.dst.row0 + r, 0, lon, lat);
+            TgtRow t;
+            t.phi = lat * B200_DEG2RAD;
+            sincos(t.phi, &t.sin_phi, &t.cos_phi);
+            t.valid = (lat >= -90.0 && lat <= 90.0) ? 1 : 0;
+            t.dlam = 0.0;
+            t.b_lo = t.b_hi = 0;
+            t.rc = t.rs = 0.0f;
+            if (t.valid) {
+                if (A.geos) {
+                    // geocentric latitude and ellipsoid radius of PROJ's geos forward, per row
+                    double pg = atan(A.rp2 * tan(t.phi));
+                    double rr = A.rp / hypot(A.rp * cos(pg), sin(pg));
+                    t.rc = (float)(rr * cos(pg));
+                    t.rs = (float)(rr * sin(pg));
+                } else {
+                    t.dlam = nn_cap_dlam(t.phi, A.theta, A.sin_theta);
+                    t.b_lo = b200_band_of(t.phi - A.theta, A.inv_dphi, A.nbands);
+                    t.b_hi = b200_band_of(t.phi + A.theta, A.inv_dphi, A.nbands);
+                }
+            }
+            t.pad = 0;
+            t.pad2 = 0.0;
+            rows[r] = t;
         }
     }
 }
 
-static int fill_query(QueryArg &Q, const b200_nn_grid_t *grid, const b200_geo_t *dst, double radius, const char *who) {
+int b200_nn_build_tables(const b200_geo_t *dst, double theta, double inv_dphi, int nbands, int geos, double lam0,
+                         double rp, double rp2, TgtCol **cols, TgtRow **rows, cudaStream_t s) {
+    *cols = nullptr;
+    *rows = nullptr;
+    B200_CUDA(cudaMallocAsync((void **)cols, (size_t)dst->width * sizeof(TgtCol), s));
+    cudaError_t e = cudaMallocAsync((void **)rows, (size_t)(dst->nrows > 0 ? dst->nrows : 1) * sizeof(TgtRow), s);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(*cols, s);
+        b200_set_error("b200_nn_query: table allocation failed: %s", cudaGetErrorString(e));
+        return B200_ENOMEM;
+    }
+    TableArg A;
+    A.dst = *dst;
+    A.theta = theta;
+    A.sin_theta = theta >= B200_HALFPI ? 1.0 : sin(theta);
+    A.inv_dphi = inv_dphi;
+    A.nbands = nbands;
+    A.geos = geos;
+    A.lam0 = lam0;
+    A.rp = rp;
+    A.rp2 = rp2;
+    nn_target_tables_kernel<<<b200_grid_for(dst->width + dst->nrows, 256, 8), 256, 0, s>>>(A, *cols, *rows);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+static int nn_bucket_query(const b200_nn_grid *grid, const b200_geo_t *dst, double radius, const QueryOut &O,
+                           cudaStream_t s) {
+    QueryArg Q;
+    Q.dst = *dst;
+    Q.G.band_off = grid->band_off;
+    Q.G.cell_start = grid->cell_start;
+    Q.G.pts = grid->pts;
+    Q.G.prefix = grid->prefix;
+    Q.G.inv_dphi = 1.0 / grid->dphi;
+    Q.G.nbands = grid->nbands;
+    Q.O = O;
+    Q.theta = b200_cap_angle(radius);
+    Q.sin_theta = Q.theta >= B200_HALFPI ? 1.0 : sin(Q.theta);
+    Q.r2 = radius * radius;
+    Q.cols = nullptr;
+    Q.rows = nullptr;
+    const int64_t n = dst->nrows * dst->width;
+    if (b200_geo_is_rectilinear(dst) && dst->width < (1LL << 30)) {
+        TgtCol *cols;
+        TgtRow *rows;
+        int rc = b200_nn_build_tables(dst, Q.theta, Q.G.inv_dphi, Q.G.nbands, 0, 0.0, 0.0, 0.0, &cols, &rows, s);
+        if (rc) return rc;
+        Q.cols = cols;
+        Q.rows = rows;
+        int64_t items = dst->nrows * ((dst->width + 255) / 256);
+        nn_bucket_query_rect_kernel<<<b200_grid_for(items, 1, 16), 256, 0, s>>>(Q);
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(cols, s);
+        cudaFreeAsync(rows, s);
+        if (e != cudaSuccess) {
+            b200_set_error("b200_nn_query: kernel launch failed: %s", cudaGetErrorString(e));
+            return B200_ECUDA;
+        }
+        return B200_OK;
+    }
+    nn_bucket_query_kernel<<<b200_grid_for(n, 256, 8), 256, 0, s>>>(Q);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+static int nn_query_dispatch(const b200_nn_grid_t *grid, const b200_geo_t *dst, double radius, const QueryOut &O,
+                             void *stream, const char *who) {
     if (grid == nullptr) {
         b200_set_error("%s: grid is NULL", who);
         return B200_EINVAL;
@@ -390,47 +543,42 @@ static int fill_query(QueryArg &Q, const b200_nn_grid_t *grid, const b200_geo_t 
         b200_set_error("%s: radius_of_influence must be positive and finite", who);
         return B200_EINVAL;
     }
-    Q.dst = *dst;
-    Q.G.band_off = grid->band_off;
-    Q.G.cell_start = grid->cell_start;
-    Q.G.pts = grid->pts;
-    Q.G.prefix = grid->prefix;
-    Q.G.inv_dphi = 1.0 / grid->dphi;
-    Q.G.nbands = grid->nbands;
-    Q.theta = cap_angle(radius);
-    Q.sin_theta = Q.theta >= B200_HALFPI ? 1.0 : sin(Q.theta);
-    Q.r2 = radius * radius;
-    return B200_OK;
+    if (dst->nrows * dst->width == 0) return B200_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (grid->mode == B200_NN_FIXED_GRID) return b200_nn_fixed_grid_query(grid, dst, radius, O, s);
+    return nn_bucket_query(grid, dst, radius, O, s);
 }
 
 extern "C" int b200_nn_query(const b200_nn_grid_t *grid, const b200_geo_t *dst, double radius, int32_t *index_array,
                              int32_t *gather_index, uint8_t *valid_output, void *stream) {
-    QueryArg Q;
-    int rc = fill_query(Q, grid, dst, radius, "b200_nn_query");
-    if (rc) return rc;
-    int64_t n = dst->nrows * dst->width;
-    if (n == 0) return B200_OK;
-    nn_query_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(Q, index_array, gather_index,
-                                                                               valid_output);
-    B200_LAUNCH_CHECK();
-    return B200_OK;
+    QueryOut O;
+    memset(&O, 0, sizeof(O));
+    O.index_array = index_array;
+    O.gather_index = gather_index;
+    O.valid_output = valid_output;
+    return nn_query_dispatch(grid, dst, radius, O, stream, "b200_nn_query");
 }
 
 extern "C" int b200_nn_query_gather_f32(const b200_nn_grid_t *grid, const b200_geo_t *dst, double radius,
                                         const float *data, float *out, int32_t nbands, int64_t src_band_stride,
                                         int64_t dst_band_stride, float fill, void *stream) {
-    QueryArg Q;
-    int rc = fill_query(Q, grid, dst, radius, "b200_nn_query_gather_f32");
-    if (rc) return rc;
     B200_CHECK_ARG(nbands >= 1, "nbands must be >= 1");
+    B200_CHECK_ARG(dst != nullptr, "geometry is NULL");
     int64_t n = dst->nrows * dst->width;
-    if (n == 0) return B200_OK;
-    B200_CHECK_ARG(data != nullptr && out != nullptr, "NULL data pointer");
-    B200_CHECK_ARG(nbands == 1 || (src_band_stride >= grid->n_src && dst_band_stride >= n), "band stride too small");
-    nn_query_gather_f32_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        Q, data, out, nbands, src_band_stride, dst_band_stride, fill);
-    B200_LAUNCH_CHECK();
-    return B200_OK;
+    if (n > 0) {
+        B200_CHECK_ARG(data != nullptr && out != nullptr, "NULL data pointer");
+        B200_CHECK_ARG(grid == nullptr || nbands == 1 || (src_band_stride >= grid->n_src && dst_band_stride >= n),
+                       "band stride too small");
+    }
+    QueryOut O;
+    memset(&O, 0, sizeof(O));
+    O.data = data;
+    O.out = out;
+    O.nbands = nbands;
+    O.src_band_stride = src_band_stride;
+    O.dst_band_stride = dst_band_stride;
+    O.fill = fill;
+    return nn_query_dispatch(grid, dst, radius, O, stream, "b200_nn_query_gather_f32");
 }
 
 // --------------------------------------------------------------------------------------- gather
@@ -478,14 +626,13 @@ nn_gather_kernel(const T *__restrict__ data, T *__restrict__ out, const int32_t 
 }
 
 template <typename T>
-static int launch_gather(const void *data, void *out, const int32_t *gidx, int64_t n_out, int nbands,
-                         int64_t src_band_stride, int64_t dst_band_stride, const void *fill, cudaStream_t s) {
+static void launch_gather(const void *data, void *out, const int32_t *gidx, int64_t n_out, int nbands,
+                          int64_t src_band_stride, int64_t dst_band_stride, const void *fill, cudaStream_t s) {
     T f;
     memcpy(&f, fill, sizeof(T));
     int64_t work = (n_out + 3) / 4;
     nn_gather_kernel<T><<<b200_grid_for(work, 256, 8), 256, 0, s>>>((const T *)data, (T *)out, gidx, n_out, nbands,
                                                                    src_band_stride, dst_band_stride, f);
-    return B200_OK;
 }
 
 extern "C" int b200_nn_gather(const void *data, void *out, const int32_t *gather_index, int64_t n_out, int32_t nbands,
@@ -542,28 +689,23 @@ extern "C" int b200_nn_compressed_to_raw(const uint8_t *valid_input, int64_t n_s
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
     int rc = B200_OK;
-    cudaError_t err = cudaSuccess;
     int64_t n_alloc = n_src > 0 ? n_src : 1;
     thrust::transform_iterator<U8ToI32, const uint8_t *> vit(valid_input, U8ToI32());
-    if ((err = cudaMalloc(&prefix, (size_t)(n_alloc + 1) * 4)) != cudaSuccess) goto fail;
-    if ((err = cudaMalloc(&raw_of, (size_t)n_alloc * 4)) != cudaSuccess) goto fail;
+    NN_TRY(cudaMalloc(&prefix, (size_t)(n_alloc + 1) * 4));
+    NN_TRY(cudaMalloc(&raw_of, (size_t)n_alloc * 4));
     // 0xff.. = -1: compressed indices >= n_valid (the kd-tree miss convention) map to "no neighbour"
-    if ((err = cudaMemsetAsync(raw_of, 0xff, (size_t)n_alloc * 4, s)) != cudaSuccess) goto fail;
+    NN_TRY(cudaMemsetAsync(raw_of, 0xff, (size_t)n_alloc * 4, s));
     if (n_src > 0) {
-        if ((err = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, vit, prefix, (int)n_src, s)) != cudaSuccess) goto fail;
-        if ((err = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) goto fail;
-        if ((err = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, vit, prefix, (int)n_src, s)) != cudaSuccess) goto fail;
+        NN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, vit, prefix, (int)n_src, s));
+        NN_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        NN_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, vit, prefix, (int)n_src, s));
         nn_raw_of_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(valid_input, prefix, n_src, raw_of);
     }
     // n_src bounds the compressed index; slots in [n_valid, n_src) still hold -1
     nn_map_index_kernel<<<b200_grid_for(n_out, 256, 8), 256, 0, s>>>(index_array, raw_of, n_src, gather_index, n_out);
-    if ((err = cudaGetLastError()) != cudaSuccess) goto fail;
-    if ((err = cudaStreamSynchronize(s)) != cudaSuccess) goto fail;
-    goto done;
+    NN_TRY(cudaGetLastError());
+    NN_TRY(cudaStreamSynchronize(s));
 fail:
-    b200_set_error("b200_nn_compressed_to_raw: %s", cudaGetErrorString(err));
-    rc = err == cudaErrorMemoryAllocation ? B200_ENOMEM : B200_ECUDA;
-done:
     cudaFree(prefix);
     cudaFree(raw_of);
     cudaFree(tmp);

@@ -17,13 +17,14 @@ import numpy as np
 from . import _lib
 from .geometry import as_geometry
 from .modifiers.geometry import _sunz_struct
-from .resample.nearest import _Grid
+from .resample.nearest import SEARCH_METHODS, _Grid
 
 
 class ABIResamplePipeline:
     """Reusable device state for resampling a stream of ABI images between two fixed geometries."""
 
-    def __init__(self, src_area, dst_area, radius_of_influence, row_window=None, src_row_window=None):
+    def __init__(self, src_area, dst_area, radius_of_influence, row_window=None, src_row_window=None,
+                 method="auto"):
         """``row_window``: band of TARGET rows this instance produces; ``src_row_window``: band of SOURCE
         rows it is fed (counts passed to ``run`` then cover only those rows) -- see satpy_b200.parallel."""
         self.torch = _lib.require_cuda()
@@ -31,6 +32,7 @@ class ABIResamplePipeline:
         self.src = as_geometry(src_area)
         self.dst = as_geometry(dst_area)
         self.radius = float(radius_of_influence)
+        self.method = SEARCH_METHODS[method]
         self.row0, self.nrows = (0, self.dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
         self.src_row0, self.src_nrows = ((0, self.src.height) if src_row_window is None else
                                          (int(src_row_window[0]), int(src_row_window[1])))
@@ -42,6 +44,10 @@ class ABIResamplePipeline:
         self.gather_index = None
         self.n_valid = None
         self.launches = 0
+        self.trace = None  # set to a list to collect (stage name, start event, end event) per stage
+
+    def _stage(self, name):
+        return _Stage(self, name)
 
     @property
     def out_shape(self):
@@ -67,8 +73,9 @@ class ABIResamplePipeline:
         n_valid = C.c_int64(0)
         handle = C.c_void_p(None)
         gs = self.src.geo_struct(self.src_row0, self.src_nrows)
-        _lib.check(self.lib.b200_nn_grid_create(C.byref(gs), None, self.radius, self.valid_input.data_ptr(),
-                                                C.byref(n_valid), C.byref(handle), _lib.stream_ptr(torch)))
+        _lib.check(self.lib.b200_nn_grid_create_ex(C.byref(gs), None, self.radius, self.valid_input.data_ptr(),
+                                                   C.byref(n_valid), C.byref(handle), self.method,
+                                                   _lib.stream_ptr(torch)))
         self.grid = _Grid(handle)
         self.n_valid = int(n_valid.value)
         self.launches += 2
@@ -117,15 +124,20 @@ class ABIResamplePipeline:
             return out
         if tuple(counts_dev.shape) != self.src_shape:
             raise ValueError(f"counts shape {tuple(counts_dev.shape)} != source window shape {self.src_shape}")
-        self.calibrate_sunz(counts_dev, cal, start_time)
+        with self._stage("calibrate_sunz"):
+            self.calibrate_sunz(counts_dev, cal, start_time)
         if reuse_neighbours:
             if self.gather_index is None:
                 self.build_grid()
                 self.query()
                 self.grid = None
-            return self.gather(self.refl, out)
-        self.build_grid()
-        self.query_gather(self.refl, out)
+            with self._stage("gather"):
+                self.gather(self.refl, out)
+            return out
+        with self._stage("build"):
+            self.build_grid()
+        with self._stage("query_gather"):
+            self.query_gather(self.refl, out)
         return out
 
     def run_host(self, counts_host, cal, start_time, out_host, out_dev=None, reuse_neighbours=False):
@@ -144,8 +156,25 @@ class ABIResamplePipeline:
         return out_host
 
 
-def _noop():  # pragma: no cover
-    pass
+class _Stage:
+    """Brackets one pipeline stage with CUDA events on the current stream when tracing is on."""
+
+    def __init__(self, pipe, name):
+        self.pipe, self.name = pipe, name
+
+    def __enter__(self):
+        if self.pipe.trace is not None:
+            torch = self.pipe.torch
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.pipe.trace is not None:
+            self.e1.record()
+            self.pipe.trace.append((self.name, self.e0, self.e1))
+        return False
 
 
 def abi_sunz_nearest(counts, cal, src_area, dst_area, start_time, radius_of_influence, row_window=None):

@@ -30,6 +30,8 @@ from ..geometry import AreaDefinition, SwathDefinition, as_geometry
 
 LOG = logging.getLogger(__name__)
 
+SEARCH_METHODS = {"auto": 0, "bucket": 1, "fixed_grid": 2}
+
 NN_COORDINATES = {"valid_input_index": ("y1", "x1"),
                   "valid_output_index": ("y2", "x2"),
                   "index_array": ("y2", "x2", "z2")}
@@ -101,13 +103,15 @@ class B200NearestResampler:
         return max(res) if res else 10000.0
 
     def precompute(self, mask=None, radius_of_influence=None, epsilon=0, cache_dir=None, row_window=None,
-                   **kwargs):
+                   method="auto", **kwargs):
         """Build the bucket grid over the valid source points and search every target pixel.
 
         ``row_window=(row0, nrows)`` restricts the search to a band of target rows (row-tiled
         multi-GPU use); the default is the whole target.  ``epsilon`` is accepted for signature
         compatibility: the search is always exact (epsilon = 0).  ``cache_dir`` is not used: the
-        neighbour info is cached in device memory on this instance.
+        neighbour info is cached in device memory on this instance.  ``method``: ``"auto"`` (fixed-grid
+        search for geostationary area sources, bucket grid otherwise), ``"bucket"`` or ``"fixed_grid"``;
+        both engines return identical indices.
         """
         del kwargs, cache_dir
         torch = _lib.require_cuda()
@@ -117,7 +121,7 @@ class B200NearestResampler:
         radius = float(radius_of_influence)
         src, dst = self.source_geo_def, self.target_geo_def
         row0, nrows = (0, dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
-        key = (radius, row0, nrows)
+        key = (radius, row0, nrows, method)
         if mask is None and key in self._index_caches:
             self._current = self._index_caches[key]
             LOG.debug("Reusing device-resident neighbour info")
@@ -136,9 +140,11 @@ class B200NearestResampler:
         n_valid = C.c_int64(0)
         handle = C.c_void_p(None)
         gs = src.geo_struct()
-        _lib.check(lib.b200_nn_grid_create(C.byref(gs), mask_ptr, radius, valid_input.data_ptr(), C.byref(n_valid),
-                                           C.byref(handle), stream))
+        _lib.check(lib.b200_nn_grid_create_ex(C.byref(gs), mask_ptr, radius, valid_input.data_ptr(),
+                                              C.byref(n_valid), C.byref(handle), SEARCH_METHODS[method], stream))
         grid = _Grid(handle)
+        used = C.c_int32(0)
+        _lib.check(lib.b200_nn_grid_method(grid.handle, C.byref(used)))
         gather_index = torch.empty((nrows, dst.width), dtype=torch.int32, device="cuda")
         index_array = torch.empty((nrows, dst.width), dtype=torch.int32, device="cuda")
         valid_output = torch.empty((nrows, dst.width), dtype=torch.uint8, device="cuda")
@@ -147,7 +153,7 @@ class B200NearestResampler:
                                      gather_index.data_ptr(), valid_output.data_ptr(), stream))
         info = {"valid_input_index": valid_input, "valid_output_index": valid_output, "index_array": index_array,
                 "gather_index": gather_index, "n_valid": int(n_valid.value), "radius": radius,
-                "row_window": (row0, nrows)}
+                "row_window": (row0, nrows), "method": {1: "bucket", 2: "fixed_grid"}[used.value]}
         del grid  # the index arrays are the complete persistent state (kdtree.py:179-182)
         if mask is None:
             self._index_caches[key] = info
@@ -244,12 +250,14 @@ class B200NearestResampler:
             while m.dim() > 2:
                 m = m.all(dim=0)
             kwargs["mask"] = m
-        pre_kw = {k: kwargs[k] for k in ("mask", "radius_of_influence", "epsilon", "row_window") if k in kwargs}
+        pre_kw = {k: kwargs[k] for k in ("mask", "radius_of_influence", "epsilon", "row_window", "method")
+                  if k in kwargs}
         self.precompute(cache_dir=cache_dir, **pre_kw)
         comp_kw = {k: v for k, v in kwargs.items() if k not in pre_kw}
         return self.compute(data, **comp_kw)
 
-    def resample_fused(self, data, radius_of_influence, fill_value=np.nan, row_window=None, out=None):
+    def resample_fused(self, data, radius_of_influence, fill_value=np.nan, row_window=None, out=None,
+                       method="auto"):
         """float32 only: search and gather in one kernel, no index array materialised.
 
         For one-off resampling of a single dataset ("fused query+gather").
@@ -271,8 +279,8 @@ class B200NearestResampler:
         n_valid = C.c_int64(0)
         handle = C.c_void_p(None)
         gs = src.geo_struct()
-        _lib.check(lib.b200_nn_grid_create(C.byref(gs), None, float(radius_of_influence), valid_input.data_ptr(),
-                                           C.byref(n_valid), C.byref(handle), stream))
+        _lib.check(lib.b200_nn_grid_create_ex(C.byref(gs), None, float(radius_of_influence), valid_input.data_ptr(),
+                                              C.byref(n_valid), C.byref(handle), SEARCH_METHODS[method], stream))
         grid = _Grid(handle)
         if out is None:
             out = torch.empty(lead + (nrows, dst.width), dtype=torch.float32, device="cuda")

