@@ -59,8 +59,9 @@ __device__ __forceinline__ int b200_cell_of(const int32_t *__restrict__ band_off
 // invalid pixel) and, for the bucket engine, the cell of every valid point.
 __global__ void __launch_bounds__(256)
 nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask,
-                        uint8_t *__restrict__ valid_input, double4 *__restrict__ rec, int32_t *__restrict__ cell_of,
-                        const int32_t *__restrict__ band_off, double inv_dphi, int nbands) {
+                        uint8_t *__restrict__ valid_input, double4 *__restrict__ rec, float4 *__restrict__ rec32,
+                        int32_t *__restrict__ cell_of, const int32_t *__restrict__ band_off, double inv_dphi,
+                        int nbands) {
     const int64_t W = S.g.width;
     const int64_t n = S.g.nrows * W;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -75,6 +76,7 @@ nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restr
         double2 *p = reinterpret_cast<double2 *>(rec + i);
         p[0] = make_double2(x, y);
         p[1] = make_double2(z, __longlong_as_double((long long)i));
+        if (rec32) rec32[i] = make_float4((float)x, (float)y, (float)z, 0.0f);
         if (cell_of) cell_of[i] = ok ? b200_cell_of(band_off, lam, phi, inv_dphi, nbands) : -1;
     }
 }
@@ -132,6 +134,7 @@ extern "C" int b200_nn_grid_destroy(b200_nn_grid_t *grid) {
     if (grid->band_off) cudaFreeAsync(grid->band_off, s);
     if (grid->cell_start) cudaFreeAsync(grid->cell_start, s);
     if (grid->pts) cudaFreeAsync(grid->pts, s);
+    if (grid->pts32) cudaFreeAsync(grid->pts32, s);
     if (grid->prefix) cudaFreeAsync(grid->prefix, s);
     cudaSetDevice(prev);
     delete grid;
@@ -223,7 +226,8 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
         NN_TRY(cudaMallocAsync((void **)&cell_of, (size_t)n_src * sizeof(int32_t), s));
     }
     NN_TRY(cudaMallocAsync((void **)&rec, (size_t)n_src * sizeof(double4), s));
-    nn_source_points_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, mask, valid_input, rec, cell_of,
+    if (!bucket) NN_TRY(cudaMallocAsync((void **)&g->pts32, (size_t)n_src * sizeof(float4), s));
+    nn_source_points_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, mask, valid_input, rec, g->pts32, cell_of,
                                                                         g->band_off, inv_dphi, nbands);
     NN_TRY(cudaGetLastError());
     rc = nn_prefix(g, valid_input, s);
@@ -231,7 +235,7 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
     if (!bucket) {
         g->pts = rec;  // the raw-indexed records ARE the search structure
         rec = nullptr;
-        g->nbytes = n_src * (int64_t)(sizeof(double4) + sizeof(int32_t));
+        g->nbytes = n_src * (int64_t)(sizeof(double4) + sizeof(float4) + sizeof(int32_t));
         goto fail;  // (common clean-up)
     }
     NN_TRY(cudaMallocAsync((void **)&g->cell_start, (size_t)(ncells + 1) * sizeof(int32_t), s));

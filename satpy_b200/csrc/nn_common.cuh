@@ -21,6 +21,7 @@ struct b200_nn_grid {
     int32_t *prefix;  // [n_src] exclusive prefix sum of valid_input: raw -> compressed index
     double4 *pts;     // bucket: [n_valid] records sorted by cell; fixed grid: [n_src] records by raw index
                       // record = {x, y, z, raw index bits}; fixed grid stores x = NaN for invalid pixels
+    float4 *pts32;    // fixed grid only: float32 copy {x, y, z, 0} by raw index (distance pre-filter)
     int64_t nbytes;
     // ---- bucket mode
     int64_t ncells;

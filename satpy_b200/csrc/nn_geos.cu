@@ -40,6 +40,7 @@ int b200_nn_fixed_grid_supported(const b200_geo_t *src) {
 
 struct GeosDev {
     const double4 *pts;
+    const float4 *pts32;   // float32 copy of the points (pre-filter)
     const int32_t *prefix;
     int32_t W, H;          // source window shape
     int32_t sweep_x, max_ring;
@@ -48,7 +49,9 @@ struct GeosDev {
     float col_scale, col_off;       // fc = angle_x * col_scale + col_off
     float row_scale, row_off;       // fr = angle_y * row_scale + row_off  (row_scale < 0)
     float vis_min;                  // targets with vx below this are on the far side beyond the margin
-    double inv_step2;               // 1 / (0.975 * min pixel size)^2
+    float inv_step;                 // 1 / (0.975 * min pixel size)
+    float radius_f;                 // radius of influence
+    float r2_slack;                 // (radius + GEOS_F32_SLACK)^2 * (1 + eps)
     double r2;
 };
 
@@ -60,44 +63,61 @@ struct GeosQueryArg {
     const TgtRow *rows;
 };
 
-__device__ __forceinline__ void nn_consider_loaded(const double2 &a, const double2 &b, double tx, double ty, double tz,
-                                                   Best &best) {
-    double d2 = b200_nn_d2(a.x, a.y, b.x, tx, ty, tz);
-    long long idx = __double_as_longlong(b.y);
-    if (d2 < best.d2 || (d2 == best.d2 && idx < best.idx)) {
-        best.d2 = d2;
-        best.idx = idx;
-    }
+// float32 squared distance to a float32 copy of a source point: a PRE-FILTER only.  Both points carry at most
+// 0.25 m of rounding per coordinate (|coordinate| < 2^23 m), so |d_f32 - d_exact| < 1 m; a candidate whose float32
+// distance exceeds the best exact distance by more than GEOS_F32_SLACK metres can never win (or tie) and is skipped
+// without touching its float64 record.  NaN (invalid pixel) fails the comparison and is skipped too.
+#define GEOS_F32_SLACK 3.0f
+__device__ __forceinline__ float nn_d2f(const float4 &p, float tx, float ty, float tz) {
+    float dx = p.x - tx, dy = p.y - ty, dz = p.z - tz;
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
-// Search around the fractional grid position (fc, fr) of a target with spherical coordinates (tx, ty, tz).
-__device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc, float fr, double tx, double ty,
-                                                     double tz) {
+// EXACT search (float64 distances, float32 pre-filter).  Out of line: it only runs for the rare targets whose
+// float32 ranking below is ambiguous (equidistant pixels, neighbour at the radius).
+__device__ __noinline__ long long nn_fixed_search_exact(const GeosDev &G, float fc, float fr, double tx, double ty,
+                                                        double tz) {
     Best best;
     best.d2 = G.r2;
     best.idx = -1;
     const float reach = (float)G.max_ring + 1.0f;
     if (!(fc > -reach) || !(fc < (float)G.W + reach) || !(fr > -reach) || !(fr < (float)G.H + reach)) return -1;
     const int c0 = (int)floorf(fc), r0 = (int)floorf(fr);
+    const float txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
+    const float nanf_ = __int_as_float(0x7fc00000);
+    const long long i00 = (long long)r0 * G.W + c0;
+    float thr2 = G.r2_slack;  // (radius + slack)^2: nothing beyond it can be accepted
     {
-        // ring 1 = the 2x2 enclosing pixels: all eight 128-bit loads are issued before the first use
+        // the 2x2 enclosing pixels: four 128-bit loads in flight together
         const bool rk0 = (unsigned)r0 < (unsigned)G.H, rk1 = (unsigned)(r0 + 1) < (unsigned)G.H;
         const bool ck0 = (unsigned)c0 < (unsigned)G.W, ck1 = (unsigned)(c0 + 1) < (unsigned)G.W;
-        const double2 *p00 = reinterpret_cast<const double2 *>(G.pts + ((long long)r0 * G.W + c0));
-        const double2 *p10 = p00 + 2 * (long long)G.W;
-        const double nan = __longlong_as_double(0x7ff8000000000000LL);
-        double2 a00 = make_double2(nan, 0.0), a01 = a00, a10 = a00, a11 = a00, b00 = a00, b01 = a00, b10 = a00, b11 = a00;
-        if (rk0 && ck0) { a00 = __ldg(p00); b00 = __ldg(p00 + 1); }
-        if (rk0 && ck1) { a01 = __ldg(p00 + 2); b01 = __ldg(p00 + 3); }
-        if (rk1 && ck0) { a10 = __ldg(p10); b10 = __ldg(p10 + 1); }
-        if (rk1 && ck1) { a11 = __ldg(p10 + 2); b11 = __ldg(p10 + 3); }
-        nn_consider_loaded(a00, b00, tx, ty, tz, best);
-        nn_consider_loaded(a01, b01, tx, ty, tz, best);
-        nn_consider_loaded(a10, b10, tx, ty, tz, best);
-        nn_consider_loaded(a11, b11, tx, ty, tz, best);
+        const float4 *q00 = G.pts32 + i00, *q10 = q00 + G.W;
+        float4 p00 = make_float4(nanf_, 0.f, 0.f, 0.f), p01 = p00, p10 = p00, p11 = p00;
+        if (rk0 && ck0) p00 = __ldg(q00);
+        if (rk0 && ck1) p01 = __ldg(q00 + 1);
+        if (rk1 && ck0) p10 = __ldg(q10);
+        if (rk1 && ck1) p11 = __ldg(q10 + 1);
+        const float d00 = nn_d2f(p00, txf, tyf, tzf), d01 = nn_d2f(p01, txf, tyf, tzf);
+        const float d10 = nn_d2f(p10, txf, tyf, tzf), d11 = nn_d2f(p11, txf, tyf, tzf);
+        const float m = fminf(fminf(d00, d01), fminf(d10, d11));  // fminf ignores NaN
+        if (m == m) {
+            const float t = sqrtf(m) + GEOS_F32_SLACK;
+            thr2 = fminf(thr2, t * t * 1.000001f);
+        }
+        // exact float64 evaluation of the few (usually one) that survive the pre-filter
+        if (d00 <= thr2) b200_nn_consider(G.pts + i00, tx, ty, tz, best);
+        if (d01 <= thr2) b200_nn_consider(G.pts + i00 + 1, tx, ty, tz, best);
+        if (d10 <= thr2) b200_nn_consider(G.pts + i00 + G.W, tx, ty, tz, best);
+        if (d11 <= thr2) b200_nn_consider(G.pts + i00 + G.W + 1, tx, ty, tz, best);
     }
     // Any closer pixel lies inside the disc of radius w pixels around (fc, fr) (Euclidean bound above).
-    const float w = sqrtf((float)(best.d2 * G.inv_step2)) * 1.0001f + GEOS_POS_ERR;
+    const float bd = sqrtf((float)best.d2);
+    const float w = bd * G.inv_step * 1.0001f + GEOS_POS_ERR;
+    if (w < 1.0f) return best.idx;  // every pixel outside the 2x2 block is at least one pixel away
+    {
+        const float t = bd * 1.000001f + GEOS_F32_SLACK;
+        thr2 = fminf(G.r2_slack, t * t * 1.000001f);
+    }
     const float w2 = w * w;
     const int rlo = max(0, (int)ceilf(fr - w)), rhi = min(G.H - 1, (int)floorf(fr + w));
     for (int r = rlo; r <= rhi; ++r) {
@@ -107,15 +127,98 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
         const float wc = sqrtf(wc2);
         const int clo = max(0, (int)ceilf(fc - wc)), chi = min(G.W - 1, (int)floorf(fc + wc));
         const bool block_row = (r == r0) || (r == r0 + 1);
+        const long long row_base = (long long)r * G.W;
         for (int c = clo; c <= chi; ++c) {
             if (block_row && (c == c0 || c == c0 + 1)) continue;  // already examined
-            b200_nn_consider(G.pts + ((long long)r * G.W + c), tx, ty, tz, best);
+            const float d = nn_d2f(__ldg(G.pts32 + row_base + c), txf, tyf, tzf);
+            if (d <= thr2) {
+                const double before = best.d2;
+                b200_nn_consider(G.pts + row_base + c, tx, ty, tz, best);
+                if (best.d2 < before) {
+                    const float t = sqrtf((float)best.d2) * 1.000001f + GEOS_F32_SLACK;
+                    thr2 = fminf(thr2, t * t * 1.000001f);
+                }
+            }
         }
     }
     return best.idx;
 }
 
-// target lon/lat -> fractional position in the source grid (PROJ geos forward, float32); false: far side
+// two smallest float32 squared distances seen so far (NaN = invalid pixel is ignored by both comparisons)
+__device__ __forceinline__ void nn_track(float d, int idx, float &m1, int &i1, float &m2) {
+    if (d < m1) {
+        m2 = m1;
+        m1 = d;
+        i1 = idx;
+    } else if (d < m2) {
+        m2 = d;
+    }
+}
+
+// Search around the fractional grid position (fc, fr) of a target with spherical coordinates (tx, ty, tz).
+// Hot path: float32 only.  e_i = float32 distance to the float32 copy of pixel i satisfies |e_i - d_i| < 1 m
+// (GEOS_F32_ERR).  If the runner-up is more than 2 m behind the leader, the leader is the exact float64 winner;
+// if the leader is more than 1 m inside (outside) the radius it is accepted (rejected) exactly as float64 would.
+// Anything closer than that is re-done by nn_fixed_search_exact.
+#define GEOS_F32_ERR 1.0f
+__device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc, float fr, double tx, double ty,
+                                                     double tz) {
+    const float reach = (float)G.max_ring + 1.0f;
+    if (!(fc > -reach) || !(fc < (float)G.W + reach) || !(fr > -reach) || !(fr < (float)G.H + reach)) return -1;
+    const int c0 = (int)floorf(fc), r0 = (int)floorf(fr);
+    const float txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
+    const float inf = __int_as_float(0x7f800000), nanf_ = __int_as_float(0x7fc00000);
+    float m1 = inf, m2 = inf;
+    int i1 = -1;
+    {
+        // the 2x2 enclosing pixels: four 128-bit loads in flight together
+        const bool rk0 = (unsigned)r0 < (unsigned)G.H, rk1 = (unsigned)(r0 + 1) < (unsigned)G.H;
+        const bool ck0 = (unsigned)c0 < (unsigned)G.W, ck1 = (unsigned)(c0 + 1) < (unsigned)G.W;
+        const int i00 = r0 * G.W + c0;
+        const float4 *q00 = G.pts32 + (long long)r0 * G.W + c0, *q10 = q00 + G.W;
+        float4 p00 = make_float4(nanf_, 0.f, 0.f, 0.f), p01 = p00, p10 = p00, p11 = p00;
+        if (rk0 && ck0) p00 = __ldg(q00);
+        if (rk0 && ck1) p01 = __ldg(q00 + 1);
+        if (rk1 && ck0) p10 = __ldg(q10);
+        if (rk1 && ck1) p11 = __ldg(q10 + 1);
+        nn_track(nn_d2f(p00, txf, tyf, tzf), i00, m1, i1, m2);
+        nn_track(nn_d2f(p01, txf, tyf, tzf), i00 + 1, m1, i1, m2);
+        nn_track(nn_d2f(p10, txf, tyf, tzf), i00 + G.W, m1, i1, m2);
+        nn_track(nn_d2f(p11, txf, tyf, tzf), i00 + G.W + 1, m1, i1, m2);
+    }
+    // Any closer pixel lies inside the disc of radius w pixels around (fc, fr) (Euclidean bound above); the exact
+    // best distance so far is at most sqrt(m1) + 1 m, and never needs to exceed the radius.
+    const float bd = fminf(G.radius_f, sqrtf(m1) + GEOS_F32_ERR);
+    const float w = bd * G.inv_step * 1.0001f + GEOS_POS_ERR;
+    if (w >= 1.0f) {  // else every pixel outside the 2x2 block is at least one pixel away
+        const float w2 = w * w;
+        const int rlo = max(0, (int)ceilf(fr - w)), rhi = min(G.H - 1, (int)floorf(fr + w));
+        for (int r = rlo; r <= rhi; ++r) {
+            const float dr = fr - (float)r;
+            const float wc2 = w2 - dr * dr;
+            if (!(wc2 >= 0.0f)) continue;
+            const float wc = sqrtf(wc2);
+            const int clo = max(0, (int)ceilf(fc - wc)), chi = min(G.W - 1, (int)floorf(fc + wc));
+            const bool block_row = (r == r0) || (r == r0 + 1);
+            const int row_base = r * G.W;
+            const float4 *row = G.pts32 + (long long)r * G.W;
+            for (int c = clo; c <= chi; ++c) {
+                if (block_row && (c == c0 || c == c0 + 1)) continue;  // already examined
+                nn_track(nn_d2f(__ldg(row + c), txf, tyf, tzf), row_base + c, m1, i1, m2);
+            }
+        }
+    }
+    if (i1 < 0) return -1;  // no valid pixel anywhere near
+    const float s1 = sqrtf(m1);
+    const float t = s1 + 2.0f * GEOS_F32_ERR + 0.01f;
+    const bool clear_winner = m2 > t * t * 1.000001f;
+    const bool clear_radius = fabsf(s1 - G.radius_f) > GEOS_F32_ERR + 0.01f;
+    if (clear_winner && clear_radius) return s1 < G.radius_f ? (long long)i1 : -1;
+    return nn_fixed_search_exact(G, fc, fr, tx, ty, tz);
+}
+
+// target lon/lat -> fractional position in the source grid (PROJ geos forward, float32); false: far side.
+// Fast reciprocal / rsqrt are fine here: only the lattice position is needed (error << GEOS_POS_ERR pixels).
 __device__ __forceinline__ bool nn_fixed_position(const GeosDev &G, float rc, float rs, float s_rel, float c_rel,
                                                   float &fc, float &fr) {
     float vx = rc * c_rel, vy = rc * s_rel, vz = rs;
@@ -123,11 +226,11 @@ __device__ __forceinline__ bool nn_fixed_position(const GeosDev &G, float rc, fl
     float tmp = G.rg - vx;
     float ax, ay;
     if (G.sweep_x) {
-        ax = atanf(vy / hypotf(vz, tmp));
-        ay = atanf(vz / tmp);
+        ax = atanf(vy * rsqrtf(fmaf(vz, vz, tmp * tmp)));
+        ay = atanf(__fdividef(vz, tmp));
     } else {
-        ax = atanf(vy / tmp);
-        ay = atanf(vz / hypotf(vy, tmp));
+        ax = atanf(__fdividef(vy, tmp));
+        ay = atanf(vz * rsqrtf(fmaf(vy, vy, tmp * tmp)));
     }
     fc = fmaf(ax, G.col_scale, G.col_off);
     fr = fmaf(ay, G.row_scale, G.row_off);
@@ -165,29 +268,75 @@ __global__ void __launch_bounds__(256) nn_fixed_query_kernel(const __grid_consta
     }
 }
 
+// per 256-column segment of a rectilinear target: the largest cos(lon - lon_0) of its columns.  A segment whose every
+// column is on the far side for a given row (rc * cmax < vis_min) is filled without any per-pixel work.
+__global__ void __launch_bounds__(256)
+nn_seg_cmax_kernel(const TgtCol *__restrict__ cols, int W, int nseg, float *__restrict__ seg_cmax) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nseg) return;
+    float m = -2.0f;
+    for (int c = warp * 256 + lane; c < min(W, warp * 256 + 256); c += 32) m = fmaxf(m, cols[c].c_rel);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) seg_cmax[warp] = m;
+}
+
 // rectilinear targets: one work item = 256 consecutive columns of one row, tables instead of trigonometry; items are
-// handed out in order through an atomic counter (chunks of GEOS_CHUNK)
-#define GEOS_CHUNK 4
+// handed out in order through an atomic counter (chunks of GEOS_CHUNK consecutive segments).
+// FUSED1: the hot configuration -- fused gather of one float32 band, no index outputs.
+#define GEOS_CHUNK 8
+template <bool FUSED1>
 __global__ void __launch_bounds__(256, 4)
-nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long long *__restrict__ queue) {
+nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long long *__restrict__ queue,
+                           const float *__restrict__ seg_cmax) {
     const int W = (int)Q.dst.width;
     const int nseg = (W + 255) >> 8;
     const long long items = (long long)Q.dst.nrows * nseg;
-    __shared__ long long s_first;
+    __shared__ int s_row, s_seg, s_count;
     for (;;) {
-        if (threadIdx.x == 0) s_first = (long long)atomicAdd(queue, (unsigned long long)GEOS_CHUNK);
+        if (threadIdx.x == 0) {
+            long long first = (long long)atomicAdd(queue, (unsigned long long)GEOS_CHUNK);
+            long long left = items - first;
+            s_count = left <= 0 ? 0 : (left < GEOS_CHUNK ? (int)left : GEOS_CHUNK);
+            if (left > 0) {
+                long long r = first / nseg;
+                s_row = (int)r;
+                s_seg = (int)(first - r * nseg);
+            }
+        }
         __syncthreads();
-        const long long first = s_first;
+        const int count = s_count;
+        int r = s_row, seg = s_seg;
         __syncthreads();
-        if (first >= items) break;
-        const long long last = min(first + GEOS_CHUNK, items);
-        for (long long it = first; it < last; ++it) {
-            int r = (int)(it / nseg);
-            int col = (int)(it - (long long)r * nseg) * 256 + threadIdx.x;
-            if (col >= W) continue;
+        if (count == 0) break;
+        for (int k = 0; k < count; ++k, ++seg) {
+            if (seg == nseg) {
+                seg = 0;
+                ++r;
+            }
             const TgtRow R = Q.rows[r];
+            const int col = seg * 256 + (int)threadIdx.x;
+            const int64_t i = (int64_t)r * W + col;
+            if (!R.valid || !(R.rc * __ldg(seg_cmax + seg) >= Q.G.vis_min)) {
+                // nothing of this segment can see the satellite: every pixel is a miss
+                if (FUSED1) {
+                    const int n = min(256, W - seg * 256);
+                    float *dst = Q.O.out + (int64_t)r * W + seg * 256;
+                    const bool aligned = (((uintptr_t)dst) & 15) == 0;
+                    if (aligned && (int)threadIdx.x * 4 + 3 < n) {
+                        st_stream_f4(dst + threadIdx.x * 4, Q.O.fill, Q.O.fill, Q.O.fill, Q.O.fill);
+                    } else if (aligned && (int)threadIdx.x * 4 < n) {
+                        for (int j = threadIdx.x * 4; j < n; ++j) st_stream_f1(dst + j, Q.O.fill);
+                    } else if (!aligned && col < W) {
+                        st_stream_f1(Q.O.out + i, Q.O.fill);
+                    }
+                } else if (col < W) {
+                    b200_nn_emit(Q.O, Q.G.prefix, i, -1, R.valid && Q.cols[col].valid);
+                }
+                continue;
+            }
+            if (col >= W) continue;
             const TgtCol Cc = Q.cols[col];
-            bool ok = R.valid && Cc.valid;
+            const bool ok = Cc.valid;
             long long raw = -1;
             float fc, fr;
             if (ok && nn_fixed_position(Q.G, R.rc, R.rs, Cc.s_rel, Cc.c_rel, fc, fr)) {
@@ -196,7 +345,10 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
                 double tz = B200_R_EARTH * R.sin_phi;
                 raw = nn_fixed_search(Q.G, fc, fr, tx, ty, tz);
             }
-            b200_nn_emit(Q.O, Q.G.prefix, (int64_t)r * W + col, raw, ok);
+            if (FUSED1)
+                st_stream_f1(Q.O.out + i, raw < 0 ? Q.O.fill : __ldg(Q.O.data + raw));
+            else
+                b200_nn_emit(Q.O, Q.G.prefix, i, raw, ok);
         }
     }
 }
@@ -212,6 +364,7 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
     Q.rows = nullptr;
     GeosDev &G = Q.G;
     G.pts = g->pts;
+    G.pts32 = g->pts32;
     G.prefix = g->prefix;
     G.W = (int32_t)src.width;
     G.H = (int32_t)src.nrows;
@@ -230,7 +383,9 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
     G.row_off = (float)((src.area.y_ul - P.y0) / src.area.pixel_size_y - (double)src.row0);
     const double ps_min = fmin(src.area.pixel_size_x, src.area.pixel_size_y);
     const double step = GEOS_BOUND_FACTOR * ps_min;
-    G.inv_step2 = 1.0 / (step * step);
+    G.inv_step = (float)(1.0 / step);
+    G.radius_f = (float)radius;
+    G.r2_slack = (float)((radius + GEOS_F32_SLACK) * (radius + GEOS_F32_SLACK) * 1.000001);
     G.r2 = radius * radius;
     double rings = ceil(radius / step + GEOS_POS_ERR);
     if (!(rings >= 1.0)) rings = 1.0;
@@ -251,14 +406,25 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
         Q.cols = cols;
         Q.rows = rows;
         unsigned long long *queue = nullptr;
+        float *seg_cmax = nullptr;
+        const int nseg = (int)((dst->width + 255) / 256);
         cudaError_t e = cudaMallocAsync((void **)&queue, sizeof(unsigned long long), s);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&seg_cmax, (size_t)nseg * sizeof(float), s);
         if (e == cudaSuccess) e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s);
         if (e == cudaSuccess) {
-            int64_t items = dst->nrows * ((dst->width + 255) / 256);
-            nn_fixed_query_rect_kernel<<<b200_grid_for((items + GEOS_CHUNK - 1) / GEOS_CHUNK, 1, 4), 256, 0, s>>>(Q, queue);
+            nn_seg_cmax_kernel<<<(nseg * 32 + 255) / 256, 256, 0, s>>>(cols, (int)dst->width, nseg, seg_cmax);
+            int64_t items = dst->nrows * (int64_t)nseg;
+            int grid = b200_grid_for((items + GEOS_CHUNK - 1) / GEOS_CHUNK, 1, 4);
+            const bool fused1 = O.out != nullptr && O.nbands == 1 && !O.index_array && !O.gather_index &&
+                                !O.valid_output;
+            if (fused1)
+                nn_fixed_query_rect_kernel<true><<<grid, 256, 0, s>>>(Q, queue, seg_cmax);
+            else
+                nn_fixed_query_rect_kernel<false><<<grid, 256, 0, s>>>(Q, queue, seg_cmax);
             e = cudaGetLastError();
         }
         if (queue) cudaFreeAsync(queue, s);
+        if (seg_cmax) cudaFreeAsync(seg_cmax, s);
         cudaFreeAsync(cols, s);
         cudaFreeAsync(rows, s);
         if (e != cudaSuccess) {
