@@ -7,7 +7,7 @@ Workload (BASELINE.json configs[4], the configuration the metric is quoted on; i
 synthetic ABI C02 10848 x 10848 int16 counts on ``goes_east_abi_f_1km`` -> reflectance [%] ->
 SunZenithCorrector -> nearest-neighbour to the 0.5 km global equirectangular grid 80150 x 40075
 (3212 Mpix, 12.85 GB float32), radius_of_influence 2000 m.  One "step" is one full pass:
-fused calibrate+sunz kernel, bucket-grid build, fused query+gather, (N > 1) one NCCL all-gather.
+fused calibrate+sunz kernel, search-structure build, fused query+gather, (N > 1) one NCCL all-gather.
 With N GPUs the target is cut into N row tiles, each rank working on the source rows that can reach
 its tile (strong scaling: the total work is fixed).
 
@@ -204,6 +204,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: satpy_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
