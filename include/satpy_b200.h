@@ -198,6 +198,27 @@ int b200_nn_query_gather_f32(const b200_nn_grid_t *grid, const b200_geo_t *dst, 
 int b200_nn_compressed_to_raw(const uint8_t *valid_input, int64_t n_src, const int32_t *index_array,
                               int32_t *gather_index, int64_t n_out, void *stream);
 
+/* ---------------------------------------------------------------- bilinear
+ * Replaces pyresample XArrayBilinearResampler.get_bil_info / get_sample_from_bil_info as driven by
+ * BilinearResampler.precompute / .compute (resample/kdtree.py:216-242, 281-293).  PARITY UNPINNED in the
+ * reference (mocked in its tests); follows the library's published algorithm (oracle/bilinear.py).
+ *   grid          a FIXED-GRID search structure (geostationary area source); B200_EUNSUPPORTED otherwise
+ *   valid_input   the uint8 array b200_nn_grid_create filled for that structure
+ *   dst           target AREA (its projection is the interpolation plane), rows [row0, +nrows)
+ *   neighbours    32 in satpy (kdtree.py:231)
+ *   index_array   out int32 [n][4] compressed indices of the UL, UR, LL, LR corner; may be NULL
+ *   gather_index  out int32 [n][4] raw source indices (-1: no valid source at all); may be NULL
+ *   t, s          out float64 [n] vertical / horizontal fractional distances, NaN = no interpolation possible
+ * Synchronises `stream` once. */
+int b200_bil_info(const b200_nn_grid_t *grid, const uint8_t *valid_input, const b200_geo_t *dst, double radius,
+                  int32_t neighbours, int32_t *index_array, int32_t *gather_index, double *t, double *s,
+                  void *stream);
+
+/* out = p1 (1-s)(1-t) + p2 s (1-t) + p3 (1-s) t + p4 s t, NaN -> fill; float32 data, float64 arithmetic. */
+int b200_bil_sample_f32(const float *data, float *out, const int32_t *gather_index, const double *t,
+                        const double *s, int64_t n_out, int32_t nbands, int64_t src_band_stride,
+                        int64_t dst_band_stride, float fill, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ listed in ``satpy.resample.base.RESAMPLER_MODULES`` (satpy/resample/base.py:77-1
 ``satpy_b200.register()`` appends this module there so that
 ``Scene.resample(area, resampler="b200_nearest")`` resolves.
 """
+from .bilinear import B200BilinearResampler  # noqa: F401
 from .nearest import NN_COORDINATES, B200NearestResampler  # noqa: F401
 
 
@@ -12,4 +13,5 @@ def get_resampler_classes():
     """Name -> class map merged into satpy's registry (same shape as satpy/resample/kdtree.py:314-320)."""
     return {
         "b200_nearest": B200NearestResampler,
+        "b200_bilinear": B200BilinearResampler,
     }

@@ -442,3 +442,81 @@ def test_pipeline_matches_oracle_and_cached_mode():
     err = np.abs(out[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-3)
     # ties may pick the other of two equidistant pixels: bounded, everything else within 1e-5
     assert (err > REL).mean() < 2e-3
+
+
+# ------------------------------------------------------------------------------------ bilinear
+# PARITY UNPINNED in the reference (satpy/tests/test_resample.py:340-416 mocks pyresample): the oracle restates the
+# library's published algorithm (oracle/bilinear.py); these tests hold the device path to that restatement.
+def _lcc_target(w=260, h=220):
+    proj = {"proj": "lcc", "lat_1": 25.0, "lat_2": 45.0, "lat_0": 35.0, "lon_0": -95.0, "ellps": "WGS84"}
+    ext = (-2.6e6, -2.2e6, 2.6e6, 2.2e6)
+    return AreaDefinition("lcc", "lcc", "lcc", proj, w, h, ext), OArea(proj, w, h, ext)
+
+
+@pytest.mark.parametrize("sscale,radius", [(500 / 5424, 100e3), (900 / 5424, 50e3)])
+def test_bilinear_matches_oracle(sscale, radius):
+    from oracle import bilinear as obil
+    from satpy_b200.resample import B200BilinearResampler
+    src, o_src = both_areas("goes_east_abi_f_2km", sscale)
+    dst, o_dst = _lcc_target()
+    r = B200BilinearResampler(src, dst)
+    r.precompute(radius_of_influence=radius)
+    info = r.bil_info()
+    t, s, vin, idx = obil.get_bil_info(o_src, o_dst, radius, 32)
+    np.testing.assert_array_equal(info["valid_input_index"], vin)
+    # same corners wherever the interpolation is defined (elsewhere the index is a don't-care: the result is fill)
+    defined = np.isfinite(t) & np.isfinite(s)
+    got_defined = np.isfinite(info["bilinear_t"]) & np.isfinite(info["bilinear_s"])
+    assert (defined != got_defined).mean() < 1e-4
+    both = defined & got_defined
+    assert both.mean() > 0.5
+    same_corners = (info["index_array"][both] == idx[both]).all(axis=1)
+    assert same_corners.mean() > 0.9999, same_corners.mean()   # equidistant ties may pick the twin pixel
+    ok = both.copy()
+    ok[both] = same_corners
+    # the quadratic (-b +- sqrt(disc)) / 2a cancels badly where opposite sides are almost parallel (a -> 0): the
+    # reference's own float64 result carries ~1e-7 of noise there, so (t, s) are held to 2e-6, not to the last bit
+    np.testing.assert_allclose(info["bilinear_t"][ok], t[ok], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(info["bilinear_s"][ok], s[ok], rtol=0, atol=2e-6)
+    assert np.median(np.abs(info["bilinear_t"][ok] - t[ok])) < 1e-12
+    data = np.random.default_rng(2).uniform(200, 320, size=(2,) + src.shape).astype(np.float32)
+    out = r.compute(data, fill_value=np.nan)
+    exp = obil.get_sample_from_bil_info(data, t, s, vin, idx, dst.shape)
+    assert out.shape == exp.shape and out.dtype == np.float32
+    okimg = ok.reshape(dst.shape)
+    np.testing.assert_allclose(out[:, okimg], exp[:, okimg], rtol=REL)
+    np.testing.assert_array_equal(np.isnan(out[:, defined.reshape(dst.shape) == got_defined.reshape(dst.shape)]),
+                                  np.isnan(exp[:, defined.reshape(dst.shape) == got_defined.reshape(dst.shape)]))
+
+
+def test_bilinear_reproduces_linear_fields():
+    """Size-independent property: a field linear in the target projection's coordinates is reproduced exactly."""
+    import torch
+    from satpy_b200.resample import B200BilinearResampler
+    src, o_src = both_areas("goes_east_abi_f_2km", 1200 / 5424)
+    dst, o_dst = _lcc_target(700, 600)
+    slon, slat = o_src.get_lonlats()
+    ix, iy = o_dst.proj.forward(slon, slat)
+    data = np.where(np.isfinite(ix), 1e-5 * ix + 2e-5 * iy + 30.0, np.nan).astype(np.float32)
+    ds = DataArrayLite(data, ("y", "x"), {"area": src, "_FillValue": -999.0})
+    res = B200BilinearResampler(src, dst).resample(ds, radius_of_influence=50e3)
+    assert res.attrs["area"] is dst and res.shape == dst.shape
+    x, y = o_dst.proj_vectors()
+    exp = 1e-5 * x[None, :] + 2e-5 * y[:, None] + 30.0
+    out = res.values
+    ok = out != -999.0
+    assert ok.mean() > 0.95
+    assert np.abs(out[ok] - exp[ok]).max() < 2e-4   # float32 data: 30..130 with 8e-6 resolution
+
+
+def test_bilinear_needs_geostationary_source_and_float32():
+    from satpy_b200.resample import B200BilinearResampler
+    src, _ = both_areas("euro_laea_1km", 100 / 5000)
+    dst, _ = _lcc_target(50, 40)
+    with pytest.raises(NotImplementedError):
+        B200BilinearResampler(src, dst).precompute()
+    gsrc, _ = both_areas("goes_east_abi_f_2km", 100 / 5424)
+    r = B200BilinearResampler(gsrc, dst)
+    r.precompute(radius_of_influence=300e3)
+    with pytest.raises(TypeError):
+        r.compute(np.zeros(gsrc.shape, np.int16))
