@@ -219,6 +219,43 @@ int b200_bil_sample_f32(const float *data, float *out, const int32_t *gather_ind
                         const double *s, int64_t n_out, int32_t nbands, int64_t src_band_stride,
                         int64_t dst_band_stride, float fill, void *stream);
 
+/* --------------------------------------------------------------------- EWA
+ * Replaces pyresample.ewa ll2cr / fornav (Cython + C++), exposed by satpy as resampler "ewa"
+ * (resample/ewa.py:3-11).  PARITY UNPINNED in the reference (no test exercises it); follows the
+ * library's published algorithm (oracle/ewa.py).  Defaults are pyresample's.
+ */
+typedef struct b200_ewa_params {
+    int32_t weight_count;        /* 10000 */
+    int32_t maximum_weight_mode; /* 0 */
+    float weight_min;            /* 0.01 */
+    float weight_distance_max;   /* 1.0  */
+    float weight_delta_max;      /* 10.0 */
+    float weight_sum_min;        /* -1.0: use weight_min */
+} b200_ewa_params_t;
+
+/* Swath lon/lat -> fractional (col, row) of the target AREA (col 0.0 / row 0.0 = centre of the top-left
+ * cell), NaN where not projectable.  cols/rows have the dtype of the swath's lon/lat arrays (float32 or
+ * float64; float64 for area sources).  points_in_grid (host, may be NULL): points with
+ * -1 <= col <= width+1 and -1 <= row <= height+1; passing it synchronises `stream`. */
+int b200_ll2cr(const b200_geo_t *swath, const b200_geo_t *dst, void *cols, void *rows,
+               int64_t *points_in_grid /* host */, void *stream);
+
+/* Add the weighted samples of float32 `data` (nbands images of swath_rows x swath_cols) to the
+ * accumulation grids grid_weights / grid_accums ([nbands][grid_rows * grid_cols] float32, zeroed by the
+ * caller before the first call; several calls -- e.g. one per scan chunk or per GPU -- accumulate).
+ * rows_per_scan <= 0 means the whole swath is one scan.  img_fill: input value to skip (NaN always is).
+ * In maximum_weight_mode all samples must come through ONE call. */
+int b200_fornav_accum(const void *cols, const void *rows, int32_t cr_is_f32, int64_t swath_rows,
+                      int64_t swath_cols, int32_t rows_per_scan, const float *data, int32_t nbands,
+                      int64_t band_stride, float img_fill, int64_t grid_rows, int64_t grid_cols,
+                      float *grid_weights, float *grid_accums, const b200_ewa_params_t *params, void *stream);
+
+/* out = sum(w v) / sum(w) where sum(w) >= weight_sum_min, else fill.  valid_counts (host, nbands entries,
+ * may be NULL): number of non-fill cells per band; passing it synchronises `stream`. */
+int b200_fornav_finalize(const float *grid_weights, const float *grid_accums, float *out, int32_t nbands,
+                         int64_t grid_size, const b200_ewa_params_t *params, float fill,
+                         int64_t *valid_counts /* host */, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

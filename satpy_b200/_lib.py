@@ -55,6 +55,11 @@ class SunzStruct(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class EwaParamsStruct(C.Structure):
+    _fields_ = [("weight_count", C.c_int32), ("maximum_weight_mode", C.c_int32), ("weight_min", C.c_float),
+                ("weight_distance_max", C.c_float), ("weight_delta_max", C.c_float), ("weight_sum_min", C.c_float)]
+
+
 _P = C.c_void_p
 _GEO = C.POINTER(GeoStruct)
 
@@ -82,6 +87,11 @@ SIGNATURES = {
     "b200_nn_compressed_to_raw": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P]),
     "b200_bil_info": (C.c_int, [_P, _P, _GEO, C.c_double, C.c_int32, _P, _P, _P, _P, _P]),
     "b200_bil_sample_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_float, _P]),
+    "b200_ll2cr": (C.c_int, [_GEO, _GEO, _P, _P, C.POINTER(C.c_int64), _P]),
+    "b200_fornav_accum": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int64,
+                                    C.c_float, C.c_int64, C.c_int64, _P, _P, C.POINTER(EwaParamsStruct), _P]),
+    "b200_fornav_finalize": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.POINTER(EwaParamsStruct), C.c_float,
+                                       C.POINTER(C.c_int64), _P]),
 }
 
 _lib = None

@@ -6,6 +6,7 @@ listed in ``satpy.resample.base.RESAMPLER_MODULES`` (satpy/resample/base.py:77-1
 ``Scene.resample(area, resampler="b200_nearest")`` resolves.
 """
 from .bilinear import B200BilinearResampler  # noqa: F401
+from .ewa import B200EWAResampler  # noqa: F401
 from .nearest import NN_COORDINATES, B200NearestResampler  # noqa: F401
 
 
@@ -14,4 +15,5 @@ def get_resampler_classes():
     return {
         "b200_nearest": B200NearestResampler,
         "b200_bilinear": B200BilinearResampler,
+        "b200_ewa": B200EWAResampler,
     }

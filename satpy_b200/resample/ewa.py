@@ -1,0 +1,116 @@
+"""``b200_ewa``: elliptical weighted averaging resampler on the device.
+
+Host-side mirror of ``pyresample.ewa.DaskEWAResampler``, which satpy registers unchanged as ``ewa``
+(satpy/resample/ewa.py:3-11): constructed as ``cls(source_geo_def, target_geo_def)``; ``precompute()`` runs ``ll2cr``
+once per geometry pair; ``compute(data, rows_per_scan=, weight_count=10000, weight_min=0.01, weight_distance_max=1.0,
+weight_delta_max=10.0, weight_sum_min=-1.0, maximum_weight_mode=False, fill_value=)`` runs ``fornav``.
+``rows_per_scan`` defaults to ``data.attrs["rows_per_scan"]`` (set by the reader,
+satpy/readers/core/viirs_atms_sdr.py:283), else the whole swath is one scan.
+Parity is UNPINNED in the reference (no test exercises ``ewa``); see oracle/ewa.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import numpy as np
+
+from .. import _lib
+from ..dataset import is_dataarray, payload, rewrap
+from ..geometry import AreaDefinition, as_geometry
+
+LOG = logging.getLogger(__name__)
+
+
+def ewa_params(weight_count=10000, weight_min=0.01, weight_distance_max=1.0, weight_delta_max=10.0,
+               weight_sum_min=-1.0, maximum_weight_mode=False) -> _lib.EwaParamsStruct:
+    p = _lib.EwaParamsStruct()
+    p.weight_count = int(weight_count)
+    p.maximum_weight_mode = 1 if maximum_weight_mode else 0
+    p.weight_min = float(weight_min)
+    p.weight_distance_max = float(weight_distance_max)
+    p.weight_delta_max = float(weight_delta_max)
+    p.weight_sum_min = float(weight_sum_min)
+    return p
+
+
+class B200EWAResampler:
+    """ll2cr + fornav; the accumulation grids live on the device for the duration of ``compute``."""
+
+    def __init__(self, source_geo_def, target_geo_def):
+        self.source_geo_def = as_geometry(source_geo_def)
+        self.target_geo_def = as_geometry(target_geo_def)
+        self._orig_target = target_geo_def
+        if not isinstance(self.target_geo_def, AreaDefinition):
+            raise NotImplementedError("the EWA target must be an AreaDefinition")
+        self._cr = None
+
+    def precompute(self, cache_dir=None, **kwargs):
+        """``ll2cr``: project every swath pixel into fractional grid coordinates; returns ``points_in_grid``."""
+        del kwargs, cache_dir
+        torch = _lib.require_cuda()
+        if self._cr is not None:
+            return self._cr["points_in_grid"]
+        src, dst = self.source_geo_def, self.target_geo_def
+        gs, gd = src.geo_struct(), dst.geo_struct()
+        f32 = bool(gs.is_swath and gs.lonlat_is_f32)
+        dtype = torch.float32 if f32 else torch.float64
+        cols = torch.empty(src.shape, dtype=dtype, device="cuda")
+        rows = torch.empty(src.shape, dtype=dtype, device="cuda")
+        n_in = C.c_int64(0)
+        _lib.check(_lib.load().b200_ll2cr(C.byref(gs), C.byref(gd), cols.data_ptr(), rows.data_ptr(), C.byref(n_in),
+                                          _lib.stream_ptr(torch)))
+        self._cr = {"cols": cols, "rows": rows, "f32": f32, "points_in_grid": int(n_in.value)}
+        return self._cr["points_in_grid"]
+
+    def compute(self, data, cache_id=None, rows_per_scan=None, fill_value=None, weight_count=10000, weight_min=0.01,
+                weight_distance_max=1.0, weight_delta_max=10.0, weight_sum_min=-1.0, maximum_weight_mode=False,
+                **kwargs):
+        del kwargs, cache_id
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        if self._cr is None:
+            self.precompute()
+        if rows_per_scan is None:
+            rows_per_scan = data.attrs.get("rows_per_scan", 0) if is_dataarray(data) else 0
+        if fill_value is None:
+            fill_value = np.nan
+        arr = payload(data)
+        was_numpy = not isinstance(arr, torch.Tensor)
+        t = torch.from_numpy(np.ascontiguousarray(arr)) if was_numpy else arr
+        if t.dtype != torch.float32:
+            raise TypeError(f"the device EWA resampler works on float32 data, got {t.dtype}")
+        t = t.to("cuda", non_blocking=True).contiguous()
+        src, dst = self.source_geo_def, self.target_geo_def
+        if tuple(t.shape[-2:]) != src.shape:
+            raise ValueError(f"data shape {tuple(t.shape)} does not end with the source shape {src.shape}")
+        lead = tuple(t.shape[:-2])
+        nbands = int(np.prod(lead)) if lead else 1
+        out = torch.empty(lead + dst.shape, dtype=torch.float32, device="cuda")
+        if self._cr["points_in_grid"] == 0:   # nothing of the swath reaches the grid: all fill, like the library
+            out.fill_(float(fill_value))
+        else:
+            weights = torch.zeros((nbands,) + dst.shape, dtype=torch.float32, device="cuda")
+            accums = torch.zeros((nbands,) + dst.shape, dtype=torch.float32, device="cuda")
+            p = ewa_params(weight_count, weight_min, weight_distance_max, weight_delta_max, weight_sum_min,
+                           maximum_weight_mode)
+            stream = _lib.stream_ptr(torch)
+            _lib.check(lib.b200_fornav_accum(self._cr["cols"].data_ptr(), self._cr["rows"].data_ptr(),
+                                             1 if self._cr["f32"] else 0, src.height, src.width, int(rows_per_scan),
+                                             t.data_ptr(), nbands, src.size, float("nan"), dst.height, dst.width,
+                                             weights.data_ptr(), accums.data_ptr(), C.byref(p), stream))
+            counts = (C.c_int64 * nbands)()
+            _lib.check(lib.b200_fornav_finalize(weights.data_ptr(), accums.data_ptr(), out.data_ptr(), nbands, dst.size,
+                                                C.byref(p), float(fill_value), counts, stream))
+            self.valid_counts = list(counts)
+        res = out.cpu().numpy() if was_numpy else out
+        if not is_dataarray(data):
+            return res
+        attrs = dict(data.attrs)
+        attrs["area"] = self._orig_target
+        return rewrap(data, res, dims=tuple(data.dims), attrs=attrs)
+
+    def resample(self, data, cache_dir=None, mask_area=None, **kwargs):
+        del mask_area
+        self.precompute(cache_dir=cache_dir)
+        return self.compute(data, **kwargs)
