@@ -163,7 +163,9 @@ int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, double radiu
                         b200_nn_grid_t **grid /* host out */, void *stream);
 /* Same, choosing the search engine: 0 = automatic, 1 = bucket grid (any source), 2 = fixed grid
  * (geostationary area sources only: the source lattice itself is the index, see csrc/nn_geos.cu;
- * B200_EUNSUPPORTED for other sources).  Both engines return identical indices. */
+ * B200_EUNSUPPORTED for other sources), 3 = fixed grid in strict mode (every lattice point of the
+ * rigorous search disc is examined; 2 rules most of them out with a local lattice model first).
+ * All engines return identical indices. */
 int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask, double radius,
                            uint8_t *valid_input, int64_t *n_valid /* host */,
                            b200_nn_grid_t **grid /* host out */, int32_t method, void *stream);

@@ -76,7 +76,8 @@ nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restr
         double2 *p = reinterpret_cast<double2 *>(rec + i);
         p[0] = make_double2(x, y);
         p[1] = make_double2(z, __longlong_as_double((long long)i));
-        if (rec32) rec32[i] = make_float4((float)x, (float)y, (float)z, 0.0f);
+        if (rec32) rec32[i] = ok ? make_float4((float)x, (float)y, (float)z, 0.0f)
+                                 : make_float4(__int_as_float(0x7f800000), 0.0f, 0.0f, 0.0f);
         if (cell_of) cell_of[i] = ok ? b200_cell_of(band_off, lam, phi, inv_dphi, nbands) : -1;
     }
 }
@@ -270,12 +271,14 @@ extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask
     B200_CHECK_ARG(grid != nullptr && n_valid != nullptr, "NULL output argument");
     B200_CHECK_ARG(valid_input != nullptr, "valid_input is NULL");
     B200_CHECK_ARG(radius > 0.0 && isfinite(radius), "radius_of_influence must be positive and finite");
-    B200_CHECK_ARG(method >= 0 && method <= 2, "method must be 0 (auto), 1 (bucket grid) or 2 (fixed grid)");
+    B200_CHECK_ARG(method >= 0 && method <= 3, "method must be 0 (auto), 1 (bucket), 2 (fixed grid) or 3 (fixed grid, strict)");
     // the structure covers the source row window [row0, row0 + nrows); indices are relative to its first pixel
     const int64_t n_src = src->nrows * src->width;
     B200_CHECK_ARG(n_src > 0, "empty source row window");
     B200_CHECK_ARG(n_src < (1LL << 31), "more than 2^31 source pixels");
     const bool fixed_ok = b200_nn_fixed_grid_supported(src) != 0;
+    const int strict = method == B200_NN_FIXED_GRID_STRICT;
+    if (strict) method = B200_NN_FIXED_GRID;
     if (method == B200_NN_FIXED_GRID && !fixed_ok) {
         b200_set_error("b200_nn_grid_create: the fixed-grid search needs a geostationary area source");
         return B200_EUNSUPPORTED;
@@ -287,6 +290,7 @@ extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask
     }
     memset(g, 0, sizeof(*g));
     g->mode = (method == 0) ? (fixed_ok ? B200_NN_FIXED_GRID : B200_NN_BUCKET) : method;
+    g->strict = strict;
     g->n_src = n_src;
     g->radius = radius;
     g->src = *src;

@@ -8,12 +8,14 @@
 
 #define B200_NN_BUCKET 1
 #define B200_NN_FIXED_GRID 2
+#define B200_NN_FIXED_GRID_STRICT 3  /* request only: a fixed-grid structure with strict = 1 */
 
 int b200_check_geo(const b200_geo_t *geo, const char *who);
 
 // One search structure over the valid points of a source geometry (opaque to the caller).
 struct b200_nn_grid {
     int mode;  // B200_NN_BUCKET or B200_NN_FIXED_GRID
+    int strict;  // fixed grid: examine every point of the rigorous disc (no lattice-model pruning)
     int device;
     void *stream;  // the stream the structure was built on; its memory is stream-ordered on it
     int64_t n_src, n_valid;

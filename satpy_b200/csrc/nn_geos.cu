@@ -44,6 +44,7 @@ struct GeosDev {
     const int32_t *prefix;
     int32_t W, H;          // source window shape
     int32_t sweep_x, max_ring;
+    int32_t prune, pad_;            // 1: rule out disc points with the local lattice model (0: strict mode)
     double lam0;
     float rg, rp2, rp, inv_rp2;     // radius_g, 1-es, sqrt(1-es), 1/(1-es)
     float col_scale, col_off;       // fc = angle_x * col_scale + col_off
@@ -144,15 +145,12 @@ __device__ __noinline__ long long nn_fixed_search_exact(const GeosDev &G, float 
     return best.idx;
 }
 
-// two smallest float32 squared distances seen so far (NaN = invalid pixel is ignored by both comparisons)
+// two smallest float32 squared distances seen so far, branch-free.  Invalid pixels are stored as (+inf, 0, 0) in the
+// float32 copy, so their distance is +inf: it never becomes the minimum and leaves the runner-up at +inf.
 __device__ __forceinline__ void nn_track(float d, int idx, float &m1, int &i1, float &m2) {
-    if (d < m1) {
-        m2 = m1;
-        m1 = d;
-        i1 = idx;
-    } else if (d < m2) {
-        m2 = d;
-    }
+    i1 = d < m1 ? idx : i1;
+    m2 = fminf(m2, fmaxf(d, m1));
+    m1 = fminf(d, m1);
 }
 
 // Search around the fractional grid position (fc, fr) of a target with spherical coordinates (tx, ty, tz).
@@ -167,16 +165,16 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
     if (!(fc > -reach) || !(fc < (float)G.W + reach) || !(fr > -reach) || !(fr < (float)G.H + reach)) return -1;
     const int c0 = (int)floorf(fc), r0 = (int)floorf(fr);
     const float txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
-    const float inf = __int_as_float(0x7f800000), nanf_ = __int_as_float(0x7fc00000);
+    const float inf = __int_as_float(0x7f800000);
     float m1 = inf, m2 = inf;
     int i1 = -1;
+    float4 p00 = make_float4(inf, 0.f, 0.f, 0.f), p01 = p00, p10 = p00, p11 = p00;
     {
         // the 2x2 enclosing pixels: four 128-bit loads in flight together
         const bool rk0 = (unsigned)r0 < (unsigned)G.H, rk1 = (unsigned)(r0 + 1) < (unsigned)G.H;
         const bool ck0 = (unsigned)c0 < (unsigned)G.W, ck1 = (unsigned)(c0 + 1) < (unsigned)G.W;
         const int i00 = r0 * G.W + c0;
         const float4 *q00 = G.pts32 + (long long)r0 * G.W + c0, *q10 = q00 + G.W;
-        float4 p00 = make_float4(nanf_, 0.f, 0.f, 0.f), p01 = p00, p10 = p00, p11 = p00;
         if (rk0 && ck0) p00 = __ldg(q00);
         if (rk0 && ck1) p01 = __ldg(q00 + 1);
         if (rk1 && ck0) p10 = __ldg(q10);
@@ -193,18 +191,68 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
     if (w >= 1.0f) {  // else every pixel outside the 2x2 block is at least one pixel away
         const float w2 = w * w;
         const int rlo = max(0, (int)ceilf(fr - w)), rhi = min(G.H - 1, (int)floorf(fr + w));
-        for (int r = rlo; r <= rhi; ++r) {
-            const float dr = fr - (float)r;
-            const float wc2 = w2 - dr * dr;
-            if (!(wc2 >= 0.0f)) continue;
-            const float wc = sqrtf(wc2);
-            const int clo = max(0, (int)ceilf(fc - wc)), chi = min(G.W - 1, (int)floorf(fc + wc));
-            const bool block_row = (r == r0) || (r == r0 + 1);
-            const int row_base = r * G.W;
-            const float4 *row = G.pts32 + (long long)r * G.W;
-            for (int c = clo; c <= chi; ++c) {
-                if (block_row && (c == c0 || c == c0 + 1)) continue;  // already examined
-                nn_track(nn_d2f(__ldg(row + c), txf, tyf, tzf), row_base + c, m1, i1, m2);
+        // Where the lattice is locally a parallelogram lattice (it is, except next to the limb), most points of that
+        // disc can be ruled out without loading them: with e_c, e_r the 3-D steps along a row / a column, the
+        // distance to lattice point (i, j) is |h|^2 + Q(i - fx, j - fy), Q the quadratic form of the Gram matrix.
+        // Only points with Q < (1.5 * best + 50 m)^2 are examined.  The model is used when all four block pixels are
+        // valid and the fourth one lies within 2 % of a pixel of where the other three predict it (the measured
+        // second-order term; over the few pixels of the disc it stays far inside the 50 % + 50 m margin).
+        bool model = G.prune && (p00.x < inf) && (p01.x < inf) && (p10.x < inf) && (p11.x < inf);
+        float gcc = 0.f, gcr = 0.f, grr = 0.f, det = 0.f, ecx = 0.f, ecy = 0.f, ecz = 0.f, erx = 0.f, ery = 0.f, erz = 0.f;
+        if (model) {
+            ecx = p01.x - p00.x, ecy = p01.y - p00.y, ecz = p01.z - p00.z;
+            erx = p10.x - p00.x, ery = p10.y - p00.y, erz = p10.z - p00.z;
+            const float dx = p11.x - (p00.x + ecx + erx), dy = p11.y - (p00.y + ecy + ery), dz = p11.z - (p00.z + ecz + erz);
+            gcc = ecx * ecx + ecy * ecy + ecz * ecz;
+            grr = erx * erx + ery * ery + erz * erz;
+            gcr = ecx * erx + ecy * ery + ecz * erz;
+            det = gcc * grr - gcr * gcr;
+            model = (dx * dx + dy * dy + dz * dz) <= 4e-4f * fminf(gcc, grr) && det > 1e-3f * gcc * grr;
+        }
+        if (model) {
+            const float d0x = txf - p00.x, d0y = tyf - p00.y, d0z = tzf - p00.z;
+            const float bc = d0x * ecx + d0y * ecy + d0z * ecz, br = d0x * erx + d0y * ery + d0z * erz;
+            const float inv_det = 1.0f / det;
+            const float fx = (bc * grr - br * gcr) * inv_det, fy = (br * gcc - bc * gcr) * inv_det;  // model position
+            const float B = 1.5f * bd + 50.0f, B2 = B * B;
+            const float hb = B * sqrtf(gcc * inv_det);
+            const int jlo = max(rlo, r0 + (int)ceilf(fy - hb)), jhi = min(rhi, r0 + (int)floorf(fy + hb));
+            const float inv_gcc = 1.0f / gcc;
+            for (int r = jlo; r <= jhi; ++r) {
+                const float b = (float)(r - r0) - fy;
+                const float disc = gcr * b * gcr * b - gcc * (grr * b * b - B2);
+                if (!(disc >= 0.0f)) continue;
+                const float sq = sqrtf(disc), mid = -gcr * b;
+                int clo = c0 + (int)ceilf(fx + (mid - sq) * inv_gcc), chi = c0 + (int)floorf(fx + (mid + sq) * inv_gcc);
+                // never outside the rigorous disc / the grid
+                const float dr = fr - (float)r;
+                const float wc2 = w2 - dr * dr;
+                if (!(wc2 >= 0.0f)) continue;
+                const float wc = sqrtf(wc2);
+                clo = max(clo, max(0, (int)ceilf(fc - wc)));
+                chi = min(chi, min(G.W - 1, (int)floorf(fc + wc)));
+                const bool block_row = (r == r0) || (r == r0 + 1);
+                const int row_base = r * G.W;
+                const float4 *row = G.pts32 + (long long)r * G.W;
+                for (int c = clo; c <= chi; ++c) {
+                    if (block_row && (c == c0 || c == c0 + 1)) continue;  // already examined
+                    nn_track(nn_d2f(__ldg(row + c), txf, tyf, tzf), row_base + c, m1, i1, m2);
+                }
+            }
+        } else {
+            for (int r = rlo; r <= rhi; ++r) {
+                const float dr = fr - (float)r;
+                const float wc2 = w2 - dr * dr;
+                if (!(wc2 >= 0.0f)) continue;
+                const float wc = sqrtf(wc2);
+                const int clo = max(0, (int)ceilf(fc - wc)), chi = min(G.W - 1, (int)floorf(fc + wc));
+                const bool block_row = (r == r0) || (r == r0 + 1);
+                const int row_base = r * G.W;
+                const float4 *row = G.pts32 + (long long)r * G.W;
+                for (int c = clo; c <= chi; ++c) {
+                    if (block_row && (c == c0 || c == c0 + 1)) continue;  // already examined
+                    nn_track(nn_d2f(__ldg(row + c), txf, tyf, tzf), row_base + c, m1, i1, m2);
+                }
             }
         }
     }
@@ -319,15 +367,15 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
             if (!R.valid || !(R.rc * __ldg(seg_cmax + seg) >= Q.G.vis_min)) {
                 // nothing of this segment can see the satellite: every pixel is a miss
                 if (FUSED1) {
-                    const int n = min(256, W - seg * 256);
-                    float *dst = Q.O.out + (int64_t)r * W + seg * 256;
-                    const bool aligned = (((uintptr_t)dst) & 15) == 0;
-                    if (aligned && (int)threadIdx.x * 4 + 3 < n) {
-                        st_stream_f4(dst + threadIdx.x * 4, Q.O.fill, Q.O.fill, Q.O.fill, Q.O.fill);
-                    } else if (aligned && (int)threadIdx.x * 4 < n) {
-                        for (int j = threadIdx.x * 4; j < n; ++j) st_stream_f1(dst + j, Q.O.fill);
-                    } else if (!aligned && col < W) {
-                        st_stream_f1(Q.O.out + i, Q.O.fill);
+                    if (threadIdx.x < 64) {  // two warps write the 1 KB of the segment, the others move on
+                        const int n = min(256, W - seg * 256);
+                        float *dst = Q.O.out + (int64_t)r * W + seg * 256;
+                        // rows are 8-byte aligned at worst (even widths): peel to a 16-byte boundary
+                        const int head = (int)(((16 - (((uintptr_t)dst) & 15)) & 15) >> 2);
+                        const int j = head + (int)threadIdx.x * 4;
+                        if (j + 3 < n) st_stream_f4(dst + j, Q.O.fill, Q.O.fill, Q.O.fill, Q.O.fill);
+                        else for (int k2 = j; k2 < n; ++k2) st_stream_f1(dst + k2, Q.O.fill);
+                        if ((int)threadIdx.x < head && (int)threadIdx.x < n) st_stream_f1(dst + threadIdx.x, Q.O.fill);
                     }
                 } else if (col < W) {
                     b200_nn_emit(Q.O, Q.G.prefix, i, -1, R.valid && Q.cols[col].valid);
@@ -365,6 +413,8 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
     GeosDev &G = Q.G;
     G.pts = g->pts;
     G.pts32 = g->pts32;
+    G.prune = g->strict ? 0 : 1;
+    G.pad_ = 0;
     G.prefix = g->prefix;
     G.W = (int32_t)src.width;
     G.H = (int32_t)src.nrows;
@@ -721,6 +771,8 @@ extern "C" int b200_bil_info(const b200_nn_grid_t *grid, const uint8_t *valid_in
     GeosDev &G = Q.G;
     G.pts = grid->pts;
     G.pts32 = grid->pts32;
+    G.prune = 0;
+    G.pad_ = 0;
     G.prefix = grid->prefix;
     G.W = (int32_t)src.width;
     G.H = (int32_t)src.nrows;

@@ -99,3 +99,23 @@ def all_gather_rows(full_image, tile_rows: int, rank: int, group=None):
     mine = full_image[rank * tile_rows:(rank + 1) * tile_rows]
     dist.all_gather_into_tensor(full_image, mine, group=group)
     return full_image
+
+
+def exchange_rows_async(full_image, tile_rows: int, rank: int, world_size: int, sub_row0: int, sub_nrows: int,
+                        group=None):
+    """Start the exchange of ONE sub-tile (rows [sub_row0, sub_row0 + sub_nrows) of every rank's tile) as a group of
+    NCCL point-to-point operations: this rank's rows go to every peer and every peer's rows land directly in their
+    final place in ``full_image`` (no staging buffer).  Lets a rank ship the sub-tiles it has finished while it still
+    computes the next one; the union over all sub-tiles is the same all-gather.  Returns the work handles."""
+    import torch.distributed as dist
+    if world_size == 1 or sub_nrows <= 0:
+        return []
+    ops = []
+    mine = full_image[rank * tile_rows + sub_row0: rank * tile_rows + sub_row0 + sub_nrows]
+    for peer in range(world_size):
+        if peer == rank:
+            continue
+        theirs = full_image[peer * tile_rows + sub_row0: peer * tile_rows + sub_row0 + sub_nrows]
+        ops.append(dist.P2POp(dist.isend, mine, peer, group))
+        ops.append(dist.P2POp(dist.irecv, theirs, peer, group))
+    return dist.batch_isend_irecv(ops)

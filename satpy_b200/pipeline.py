@@ -81,10 +81,12 @@ class ABIResamplePipeline:
         self.launches += 2
         return self.grid
 
-    def query_gather(self, data, out, fill=float("nan")):
-        """Fused search + gather of float32 ``data`` into ``out``; one launch."""
+    def query_gather(self, data, out, fill=float("nan"), row_window=None):
+        """Fused search + gather of float32 ``data`` into ``out``; one launch.  ``row_window``: a sub-band of this
+        instance's target rows (``out`` then holds just those rows)."""
         torch = self.torch
-        gd = self.dst.geo_struct(self.row0, self.nrows)
+        r0, n = (self.row0, self.nrows) if row_window is None else (int(row_window[0]), int(row_window[1]))
+        gd = self.dst.geo_struct(r0, n)
         _lib.check(self.lib.b200_nn_query_gather_f32(self.grid.handle, C.byref(gd), self.radius, data.data_ptr(),
                                                      out.data_ptr(), 1, self.refl.numel(), out.numel(), fill,
                                                      _lib.stream_ptr(torch)))

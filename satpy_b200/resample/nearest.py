@@ -30,7 +30,7 @@ from ..geometry import AreaDefinition, SwathDefinition, as_geometry
 
 LOG = logging.getLogger(__name__)
 
-SEARCH_METHODS = {"auto": 0, "bucket": 1, "fixed_grid": 2}
+SEARCH_METHODS = {"auto": 0, "bucket": 1, "fixed_grid": 2, "fixed_grid_strict": 3}
 
 NN_COORDINATES = {"valid_input_index": ("y1", "x1"),
                   "valid_output_index": ("y2", "x2"),
@@ -153,7 +153,7 @@ class B200NearestResampler:
                                      gather_index.data_ptr(), valid_output.data_ptr(), stream))
         info = {"valid_input_index": valid_input, "valid_output_index": valid_output, "index_array": index_array,
                 "gather_index": gather_index, "n_valid": int(n_valid.value), "radius": radius,
-                "row_window": (row0, nrows), "method": {1: "bucket", 2: "fixed_grid"}[used.value]}
+                "row_window": (row0, nrows), "method": {1: "bucket", 2: "fixed_grid"}[used.value] + ("_strict" if method == "fixed_grid_strict" else "")}
         del grid  # the index arrays are the complete persistent state (kdtree.py:179-182)
         if mask is None:
             self._index_caches[key] = info

@@ -329,14 +329,32 @@ def test_nearest_engines_agree_exactly(dname, dscale, radius):
     src, _ = both_areas("goes_east_abi_f_2km", 900 / 5424)   # 12 km pixels
     dst, _ = both_areas(dname, dscale)
     out = {}
-    for method in ("bucket", "fixed_grid"):
+    for method in ("bucket", "fixed_grid", "fixed_grid_strict"):
         r = B200NearestResampler(src, dst)
         r.precompute(radius_of_influence=radius, method=method)
         out[method] = r.neighbour_info()
     for k in NN_KEYS:
         np.testing.assert_array_equal(out["bucket"][k], out["fixed_grid"][k])
+        np.testing.assert_array_equal(out["bucket"][k], out["fixed_grid_strict"][k])
     hit = (out["bucket"]["index_array"] >= 0).mean()
     assert 0.0 < hit < 1.0
+
+
+def test_fixed_grid_pruning_is_exact_on_the_full_disk():
+    """The lattice-model pruning of the fixed-grid search against its strict mode over a whole (coarse) full disk seen
+    from a fine global grid -- nadir, mid-latitudes and the limb, where pixels stretch to many times their nadir size --
+    and against SEVIRI's sweep-y geometry."""
+    for sname, sscale, dname, dscale, radius in (("goes_east_abi_f_1km", 2000 / 10848, "global_eqc_500m", 6000 / 80150, 11e3),
+                                                 ("msg_seviri_fes_3km", 1500 / 3712, "global_eqc_500m", 5000 / 80150, 16e3)):
+        src, _ = both_areas(sname, sscale)
+        dst, _ = both_areas(dname, dscale)
+        out = {}
+        for method in ("fixed_grid", "fixed_grid_strict"):
+            r = B200NearestResampler(src, dst)
+            r.precompute(radius_of_influence=radius, method=method)
+            out[method] = r._current["gather_index"].clone()
+        assert bool((out["fixed_grid"] == out["fixed_grid_strict"]).all())
+        assert 0.2 < float((out["fixed_grid"] >= 0).float().mean()) < 0.6
 
 
 def test_fixed_grid_rejects_non_geos_sources():
