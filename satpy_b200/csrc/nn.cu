@@ -599,6 +599,7 @@ nn_gather_kernel(const T *__restrict__ data, T *__restrict__ out, const int32_t 
     // four consecutive outputs per thread: one 128-bit index load, four independent source loads in
     // flight, and (for 4-byte elements) one 128-bit store
     const int64_t n4 = n_out >> 2;
+    const bool out_aligned = (((uintptr_t)out) & 15) == 0;  // else (e.g. a row band of an odd-width image): scalar stores
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
         int4 ix = ld_stream_v4(gidx + 4 * q);
@@ -609,7 +610,7 @@ nn_gather_kernel(const T *__restrict__ data, T *__restrict__ out, const int32_t 
             T v2 = ix.z < 0 ? fill : __ldg(src + ix.z);
             T v3 = ix.w < 0 ? fill : __ldg(src + ix.w);
             T *dst = out + b * dst_band_stride + 4 * q;
-            if (sizeof(T) == 4 && ((dst_band_stride & 3) == 0 || nbands == 1)) {
+            if (sizeof(T) == 4 && out_aligned && ((dst_band_stride & 3) == 0 || nbands == 1)) {
                 int4 w;
                 w.x = *reinterpret_cast<int *>(&v0);
                 w.y = *reinterpret_cast<int *>(&v1);
@@ -653,7 +654,8 @@ extern "C" int b200_nn_gather(const void *data, void *out, const int32_t *gather
     if (n_out == 0) return B200_OK;
     B200_CHECK_ARG(data != nullptr && out != nullptr && gather_index != nullptr, "NULL data pointer");
     B200_CHECK_ARG(((uintptr_t)gather_index & 15) == 0, "gather_index must be 16-byte aligned");
-    B200_CHECK_ARG(elem_size != 4 || ((uintptr_t)out & 15) == 0, "out must be 16-byte aligned");
+    B200_CHECK_ARG(((uintptr_t)out & (uintptr_t)(elem_size - 1)) == 0 && ((uintptr_t)data & (uintptr_t)(elem_size - 1)) == 0,
+                   "data and out must be aligned to the element size");
     B200_CHECK_ARG(nbands == 1 || dst_band_stride >= n_out, "band stride smaller than one image");
     cudaStream_t s = (cudaStream_t)stream;
     switch (elem_size) {

@@ -142,19 +142,39 @@ class ABIResamplePipeline:
             self.query_gather(self.refl, out)
         return out
 
-    def run_host(self, counts_host, cal, start_time, out_host, out_dev=None, reuse_neighbours=False):
-        """``run`` with HOST buffers (pinned torch tensors or numpy arrays): counts are copied to the device,
-        the image is copied back into ``out_host``; returns after the copy has completed."""
+    def run_host(self, counts_host, cal, start_time, out_host, out_dev=None, chunks=8):
+        """``run`` with HOST buffers (pinned torch tensors or numpy arrays): counts are copied to the device, the image
+        is copied back into ``out_host``; returns after the last copy has completed.  The target rows are searched in
+        ``chunks`` bands and each band starts its device->host copy (second stream) while the next one is searched."""
         torch = self.torch
         c = counts_host if isinstance(counts_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(counts_host))
         o = out_host if isinstance(out_host, torch.Tensor) else torch.from_numpy(out_host)
+        if self.nrows == 0:
+            return out_host
+        if out_dev is None:
+            out_dev = torch.empty(self.out_shape, dtype=torch.float32, device="cuda")
+        if self.src_nrows == 0:
+            out_dev.fill_(float("nan"))
+            o.copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_host
         if getattr(self, "_counts_dev", None) is None:
             self._counts_dev = torch.empty(self.src_shape, dtype=torch.int16, device="cuda")
-        if c.numel():
-            self._counts_dev.copy_(c.view(torch.int16) if c.dtype == torch.uint16 else c, non_blocking=True)
-        out = self.run(self._counts_dev, cal, start_time, out=out_dev, reuse_neighbours=reuse_neighbours)
-        o.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            self._copy_stream = torch.cuda.Stream()
+        self._counts_dev.copy_(c.view(torch.int16) if c.dtype == torch.uint16 else c, non_blocking=True)
+        self.calibrate_sunz(self._counts_dev, cal, start_time)
+        self.build_grid()
+        main = torch.cuda.current_stream()
+        rows = -(-self.nrows // max(1, chunks))
+        for r0 in range(0, self.nrows, rows):
+            n = min(rows, self.nrows - r0)
+            self.query_gather(self.refl, out_dev[r0:r0 + n], row_window=(self.row0 + r0, n))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ev)
+                o[r0:r0 + n].copy_(out_dev[r0:r0 + n], non_blocking=True)
+        self._copy_stream.synchronize()
         return out_host
 
 

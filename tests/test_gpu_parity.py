@@ -625,3 +625,27 @@ def test_fornav_properties():
         r.compute(const, rows_per_scan=7)      # swath rows not a multiple of rows_per_scan
     with pytest.raises(ValueError):
         r.compute(const, rows_per_scan=rps, weight_min=0.0)
+
+
+def test_gather_into_misaligned_row_band():
+    """Row bands of an image whose width is not a multiple of 4 start at addresses that are only 4- or 8-byte aligned
+    (the multi-GPU decomposition writes such bands): the gather and the fused search must handle them."""
+    import torch
+    from satpy_b200.pipeline import ABIResamplePipeline
+    s, d = 300 / 10848, 602 / 80150      # target width 602: 602 * 4 B = 8 (mod 16)
+    src, dst = demo.make_area("goes_east_abi_f_1km", s), demo.make_area("global_eqc_500m", d)
+    assert dst.width % 4 == 2
+    counts = torch.from_numpy(demo.abi_counts(src.shape, seed=7, band="C02")).cuda()
+    cal = demo.abi_calibration("C02")
+    radius = 2.5 * 1002.0 / s
+    ref = ABIResamplePipeline(src, dst, radius).run(counts, cal, demo.START_TIME).cpu().numpy()
+    full = torch.full((dst.height, dst.width), -7.0, dtype=torch.float32, device="cuda")
+    for row0, nrows in ((0, 101), (101, 37), (138, dst.height - 138)):   # 101 * 602 is odd-aligned
+        pipe = ABIResamplePipeline(src, dst, radius, row_window=(row0, nrows))
+        view = full[row0:row0 + nrows]
+        pipe.run(counts, cal, demo.START_TIME, out=view)
+        np.testing.assert_array_equal(view.cpu().numpy(), ref[row0:row0 + nrows])
+        pipe.query()
+        view.fill_(-7.0)
+        pipe.gather(pipe.refl, view)
+        np.testing.assert_array_equal(view.cpu().numpy(), ref[row0:row0 + nrows])
