@@ -9,6 +9,7 @@
 #define B200_NUM_SMS 148
 
 void b200_set_error(const char *fmt, ...);
+void b200_pool_keep_memory();
 
 #define B200_CHECK_ARG(cond, msg)                         \
     do {                                                  \

@@ -14,6 +14,20 @@ void b200_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// Keep freed stream-ordered allocations in the default memory pool instead of returning them to the driver at every
+// synchronisation: temporaries (projection tables, search structures) are re-allocated for every scene.
+void b200_pool_keep_memory() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
+}
+
 extern "C" const char *b200_version(void) { return "satpy_b200 0.1.0 (sm_100a)"; }
 
 extern "C" const char *b200_last_error(void) { return g_err; }
@@ -33,6 +47,7 @@ extern "C" int b200_device_count(int *count) {
 }
 
 int b200_check_geo(const b200_geo_t *geo, const char *who) {
+    b200_pool_keep_memory();  // every entry point that allocates temporaries validates a geometry first
     if (geo == nullptr) {
         b200_set_error("%s: geometry is NULL", who);
         return B200_EINVAL;

@@ -23,6 +23,7 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include "nn_common.cuh"
+#include "b200_geos_fast.cuh"
 
 #define B200_NN_MAX_CELLS (160LL * 1000 * 1000)
 
@@ -61,18 +62,32 @@ __global__ void __launch_bounds__(256)
 nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask,
                         uint8_t *__restrict__ valid_input, double4 *__restrict__ rec, float4 *__restrict__ rec32,
                         int32_t *__restrict__ cell_of, const int32_t *__restrict__ band_off, double inv_dphi,
-                        int nbands) {
+                        int nbands, const __grid_constant__ GeosFast F) {
     const int64_t W = S.g.width;
     const int64_t n = S.g.nrows * W;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        double lon, lat;
-        b200_geo_lonlat(S.g, S.g.row0 + r, i - r * W, lon, lat);
-        bool ok = b200_lonlat_valid(lon, lat) && !(mask != nullptr && mask[i]);
-        valid_input[i] = ok ? 1 : 0;
         double x = __longlong_as_double(0x7ff8000000000000LL), y = 0.0, z = 0.0, lam = 0.0, phi = 0.0;
-        if (ok) b200_lonlat2xyz(lon, lat, x, y, z, lam, phi);
+        bool ok;
+        if (F.enabled) {
+            // geostationary source: every pixel on the disk has a valid lon/lat; the point comes from the view
+            // vector without trigonometric functions (the angles are only needed to pick a bucket cell)
+            double sl, cl, sp, cp;
+            ok = geos_fast_xyz(F, S.g.row0 + r, i - r * W, B200_R_EARTH, x, y, z, sl, cl, sp, cp) &&
+                 !(mask != nullptr && mask[i]);
+            if (!ok) x = __longlong_as_double(0x7ff8000000000000LL);
+            if (ok && cell_of) {
+                lam = atan2(sl, cl);
+                phi = atan2(sp, cp);
+            }
+        } else {
+            double lon, lat;
+            b200_geo_lonlat(S.g, S.g.row0 + r, i - r * W, lon, lat);
+            ok = b200_lonlat_valid(lon, lat) && !(mask != nullptr && mask[i]);
+            if (ok) b200_lonlat2xyz(lon, lat, x, y, z, lam, phi);
+        }
+        valid_input[i] = ok ? 1 : 0;
         double2 *p = reinterpret_cast<double2 *>(rec + i);
         p[0] = make_double2(x, y);
         p[1] = make_double2(z, __longlong_as_double((long long)i));
@@ -111,21 +126,9 @@ struct U8ToI32 {
     __host__ __device__ __forceinline__ int32_t operator()(const uint8_t &v) const { return (int32_t)v; }
 };
 
-// Device memory of a search structure comes from the stream-ordered pool: after the first build, rebuilding for the
-// next scene allocates without a device synchronisation.  All uses of a structure must be on the stream it was
-// created on (the caller's current stream).
-static void nn_pool_keep_memory() {
-    static bool done = false;
-    if (done) return;
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    done = true;
-}
-
+// Device memory of a search structure comes from the stream-ordered pool (b200_pool_keep_memory, lib.cu): after the
+// first build, rebuilding for the next scene allocates without a device synchronisation.  All uses of a structure must
+// be on the stream it was created on (the caller's current stream).
 extern "C" int b200_nn_grid_destroy(b200_nn_grid_t *grid) {
     if (grid == nullptr) return B200_OK;
     int prev = 0;
@@ -193,7 +196,9 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
     double inv_dphi = 1.0;
     SrcArg S;
     S.g = *src;
-    nn_pool_keep_memory();
+    GeosFast fast;
+    memset(&fast, 0, sizeof(fast));
+    b200_pool_keep_memory();
     if (bucket) {
         // ---- host: band layout.  Band height >= cap angle; widened if the table would get too large.
         double dphi = b200_cap_angle(g->radius);
@@ -228,9 +233,12 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
     }
     NN_TRY(cudaMallocAsync((void **)&rec, (size_t)n_src * sizeof(double4), s));
     if (!bucket) NN_TRY(cudaMallocAsync((void **)&g->pts32, (size_t)n_src * sizeof(float4), s));
+    rc = b200_geos_fast_prepare(src, &fast, s);
+    if (rc) goto fail;
     nn_source_points_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, mask, valid_input, rec, g->pts32, cell_of,
-                                                                        g->band_off, inv_dphi, nbands);
+                                                                        g->band_off, inv_dphi, nbands, fast);
     NN_TRY(cudaGetLastError());
+    b200_geos_fast_release(&fast, s);
     rc = nn_prefix(g, valid_input, s);
     if (rc) goto fail;
     if (!bucket) {
@@ -257,6 +265,7 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
     g->nbytes = (int64_t)(nbands + 1) * 4 + (ncells + 1) * 4 + n_src * 4 + (g->n_valid > 0 ? g->n_valid : 1) * 32;
 fail:
     delete[] h_off;
+    b200_geos_fast_release(&fast, s);
     if (counts) cudaFreeAsync(counts, s);
     if (cell_of) cudaFreeAsync(cell_of, s);
     if (rec) cudaFreeAsync(rec, s);

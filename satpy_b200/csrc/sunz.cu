@@ -15,11 +15,13 @@
 #include "b200_common.cuh"
 #include "b200_proj.cuh"
 #include "b200_cal.cuh"
+#include "b200_geos_fast.cuh"
 
 #define B200_DEG2RAD_F 0.017453292f  // numpy's float32 deg2rad factor
 
 struct SunzDev {
     b200_geo_t geo;
+    GeosFast fast;  // geostationary areas: table-driven inverse projection
     double gmst, ra, sin_dec, cos_dec;
     double limit_rad, limit_cos, max_rad, max_cos, span, li_lim;
     int32_t has_max, lonlat_f32, method, pad;
@@ -27,7 +29,7 @@ struct SunzDev {
 
 __device__ __forceinline__ double b200_cos_sza_pixel(const SunzDev &S, int64_t row, int64_t col) {
     double lon, lat;
-    bool ok = b200_geo_lonlat(S.geo, row, col, lon, lat);
+    bool ok = S.fast.enabled ? geos_fast_lonlat(S.fast, row, col, lon, lat) : b200_geo_lonlat(S.geo, row, col, lon, lat);
     if (!ok || !(lon < 1e30) || !(lat < 1e30)) return __longlong_as_double(0x7ff8000000000000LL);
     double sl, cl, lon_r;
     if (S.lonlat_f32) {
@@ -151,6 +153,7 @@ abi_vis_sunz_kernel(const __grid_constant__ FusedBands B, const __grid_constant_
 }
 
 static int fill_sunz(SunzDev &S, const b200_geo_t *geo, const b200_sunz_t *sz, bool need_geo) {
+    memset(&S.fast, 0, sizeof(S.fast));
     if (need_geo) {
         B200_CHECK_ARG(geo != nullptr, "geo is NULL");
         B200_CHECK_ARG(geo->width > 0 && geo->height > 0, "empty geometry");
@@ -190,7 +193,10 @@ extern "C" int b200_cos_sza(const b200_geo_t *geo, const b200_sunz_t *sz, double
     int64_t n = geo->nrows * geo->width;
     if (n == 0) return B200_OK;
     B200_CHECK_ARG(cos_sza != nullptr, "NULL output");
+    rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
+    if (rc) return rc;
     cos_sza_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(cos_sza, S);
+    b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -205,8 +211,11 @@ extern "C" int b200_sunz_correct(const float *data, float *out, int32_t nbands, 
     if (n == 0) return B200_OK;
     B200_CHECK_ARG(data != nullptr && out != nullptr, "NULL data pointer");
     B200_CHECK_ARG(nbands == 1 || band_stride >= n, "band stride smaller than one image");
+    rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
+    if (rc) return rc;
     sunz_correct_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands,
                                                                                   band_stride, S);
+    b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -246,7 +255,10 @@ extern "C" int b200_abi_vis_sunz(const int16_t *const *counts, float *const *out
             B200_CHECK_ARG(cal[b].mode == 1, "fused kernel is for reflectance calibration (mode 1)");
         }
     }
+    rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
+    if (rc) return rc;
     abi_vis_sunz_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
+    b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
