@@ -361,11 +361,24 @@ def run_b200(args):
 
     peak, peak_src = measured_peak()
     roofline = None
+    traffic_by_kernel, traffic_src = {}, None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload (N = 1)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        traffic_by_kernel, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     if stages:
         kernels = {k: v for k, v in stages.items() if k in ("calibrate_sunz", "query_gather")}
         top = max(kernels, key=lambda k: kernels[k]["ms"])
+        traffic = None
+        if world == 1 and args.scale == 1.0:
+            for name, nbytes in traffic_by_kernel.items():
+                if name.replace("void ", "").split("<")[0] in stages[top]["kernel"]:
+                    traffic = nbytes
         roofline = {"kernel": stages[top]["kernel"], "bound": "hbm", "achieved": stages[top]["gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": stages[top]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": stages[top]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes": stages[top]["algorithmic_bytes"], "peak_source": peak_src,
                     "share_of_step": stages[top]["ms"] / ms_step,
                     "note": "algorithmic bytes / CUDA-event time of the dominant kernel on rank 0, in situ; the kernel is "
                             "instruction-issue bound, not HBM bound (profiles/); the HBM-bound kernel of this path is "
