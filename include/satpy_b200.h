@@ -105,6 +105,47 @@ typedef struct b200_abi_cal {
 int b200_abi_calibrate(const int16_t *counts, float *out, int64_t n,
                        const b200_abi_cal_t *cal /* host */, void *stream);
 
+/* AHI HSD (readers/ahi_hsd.py:607-611,675-750): uint16 counts -> radiance / reflectance [%] / BT [K].
+ * The Planck constants are doubles; bt_in_f64 selects numpy's dtype flow when they are numpy float64
+ * scalars (a real file header: float64 arithmetic) or Python floats (float32 arithmetic). */
+typedef struct b200_ahi_cal {
+    int32_t mode;          /* 0 radiance, 1 reflectance, 2 brightness temperature            */
+    int32_t has_invalid;   /* mask count_outside_scan / count_error (-> NaN)                 */
+    int32_t count_outside_scan, count_error;
+    int32_t bt_in_f64, reserved;
+    float gain, offset;    /* float32(dn_gain), float32(dn_offset)                           */
+    float coeff, pad;      /* float32(coeff_rad2albedo_conversion)                           */
+    double a;              /* h c / (k cwl)                                                  */
+    double num;            /* 2 h c^2                                                        */
+    double cwl5;           /* cwl^5, cwl = central_wave_length * 1e-6                        */
+    double c0, c1, c2;     /* rad2tb polynomial                                              */
+} b200_ahi_cal_t;
+
+int b200_ahi_calibrate(const uint16_t *counts, float *out, int64_t n, const b200_ahi_cal_t *cal /* host */,
+                       void *stream);
+
+/* SEVIRI (readers/core/seviri.py:574-633,660-686): counts (float32 or uint16) -> radiance / reflectance
+ * [%] / BT [K].  All constants already rounded to float32 by the host (numpy weak-scalar rule). */
+typedef struct b200_seviri_cal {
+    int32_t mode;          /* 0 radiance, 1 reflectance, 2 BT from effective, 3 BT from spectral radiance */
+    int32_t reserved;
+    float gain, offset;
+    float pi_f, solar_irradiance, sun_earth_dist2; /* float32(pi), F, float32(d*d)            */
+    float c1, nu3, c2nu;   /* float32(C1), float32(nu^3), float32(C2 * nu)                   */
+    float alpha, beta;     /* effective radiance: (T - beta) / alpha                          */
+    float fit_a, fit_b, fit_c; /* spectral radiance: a T^2 + b T + c (BTFIT)                  */
+} b200_seviri_cal_t;
+
+int b200_seviri_calibrate(const void *counts, int32_t counts_are_f32, float *out, int64_t n,
+                          const b200_seviri_cal_t *cal /* host */, void *stream);
+
+/* VIIRS SDR (readers/core/viirs_atms_sdr.py:197-214,328-361): fill masking (ints >= fill_min_int, floats
+ * <= fill_max_float -> NaN) then data * factor + offset with one pair per granule of rows.
+ * factors: host, n_granules x 2 float32; rows_per_granule: host, n_granules.  Synchronises `stream`. */
+int b200_viirs_scale(const void *data, int32_t data_is_f32, float *out, int64_t rows, int64_t cols,
+                     const float *factors /* host */, const int32_t *rows_per_granule /* host */,
+                     int32_t n_granules, int32_t fill_min_int, float fill_max_float, void *stream);
+
 /* ------------------------------------------------------------- sun zenith
  * get_cos_sza (modifiers/angles.py:418-469, pyorbital cos_zen) and
  * _sunzen_corr_cos_ndarray (modifiers/angles.py:555-584) as driven by
@@ -132,6 +173,10 @@ int b200_sunz_correct(const float *data, float *out, int32_t nbands, int64_t ban
  * modifiers/geometry.py:64-66); sza is float32, one image shared by all bands. */
 int b200_sunz_correct_sza(const float *data, const float *sza_deg, float *out, int32_t nbands,
                           int64_t band_stride, int64_t n, const b200_sunz_t *sz, void *stream);
+
+/* SunZenithReducer (modifiers/geometry.py:166-207 -> angles.py:594-624): out = data * reduction(sza). */
+int b200_sunz_reduce(const float *data, const float *sunz_deg, float *out, int32_t nbands, int64_t band_stride,
+                     int64_t n, float limit_deg, float max_sza_deg, float strength, void *stream);
 
 /* Fused reader calibration + SunZenithCorrector for up to 4 ABI reflective bands
  * sharing one area: counts -> radiance -> reflectance[%] -> * corr.  6 B/pixel/band. */

@@ -55,6 +55,21 @@ class SunzStruct(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class AhiCalStruct(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("has_invalid", C.c_int32), ("count_outside_scan", C.c_int32),
+                ("count_error", C.c_int32), ("bt_in_f64", C.c_int32), ("reserved", C.c_int32),
+                ("gain", C.c_float), ("offset", C.c_float), ("coeff", C.c_float), ("pad", C.c_float),
+                ("a", C.c_double), ("num", C.c_double), ("cwl5", C.c_double),
+                ("c0", C.c_double), ("c1", C.c_double), ("c2", C.c_double)]
+
+
+class SeviriCalStruct(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("gain", C.c_float), ("offset", C.c_float),
+                ("pi_f", C.c_float), ("solar_irradiance", C.c_float), ("sun_earth_dist2", C.c_float),
+                ("c1", C.c_float), ("nu3", C.c_float), ("c2nu", C.c_float), ("alpha", C.c_float), ("beta", C.c_float),
+                ("fit_a", C.c_float), ("fit_b", C.c_float), ("fit_c", C.c_float)]
+
+
 class EwaParamsStruct(C.Structure):
     _fields_ = [("weight_count", C.c_int32), ("maximum_weight_mode", C.c_int32), ("weight_min", C.c_float),
                 ("weight_distance_max", C.c_float), ("weight_delta_max", C.c_float), ("weight_sum_min", C.c_float)]
@@ -70,6 +85,11 @@ SIGNATURES = {
     "b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "b200_area_lonlats": (C.c_int, [_GEO, _P, _P, _P]),
     "b200_abi_calibrate": (C.c_int, [_P, _P, C.c_int64, C.POINTER(AbiCalStruct), _P]),
+    "b200_ahi_calibrate": (C.c_int, [_P, _P, C.c_int64, C.POINTER(AhiCalStruct), _P]),
+    "b200_seviri_calibrate": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(SeviriCalStruct), _P]),
+    "b200_viirs_scale": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                                   C.c_int32, C.c_int32, C.c_float, _P]),
+    "b200_sunz_reduce": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, _P]),
     "b200_cos_sza": (C.c_int, [_GEO, C.POINTER(SunzStruct), _P, _P]),
     "b200_sunz_correct": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _GEO, C.POINTER(SunzStruct), _P]),
     "b200_sunz_correct_sza": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.POINTER(SunzStruct), _P]),

@@ -1,3 +1,3 @@
 """Modifier plug-ins of the B200 hot path (same class names as ``satpy.modifiers``)."""
 from .geometry import (EffectiveSolarPathLengthCorrector, IncompatibleAreas, SunZenithCorrector,  # noqa: F401
-                       cos_sza, sunz_correct)
+                       SunZenithReducer, cos_sza, sunz_correct, sunz_reduce)

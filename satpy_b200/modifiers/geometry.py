@@ -195,3 +195,51 @@ class EffectiveSolarPathLengthCorrector(_SunZenithCorrectorBase):
 
     def _limit(self):
         return self.correction_limit
+
+
+def sunz_reduce(data, sza, limit=55.0, max_sza=90.0, strength=1.5, out=None):
+    """``sunzen_reduction`` (satpy/modifiers/angles.py:587-624): ``data * reduction(sza)``; float32 data and SZA [deg]."""
+    torch = _lib.require_cuda()
+    t, was_numpy = _to_cuda_f32(torch, data)
+    z, _ = _to_cuda_f32(torch, sza)
+    if t.dim() not in (2, 3) or tuple(z.shape) != tuple(t.shape[-2:]):
+        raise IncompatibleAreas(f"sza shape {tuple(z.shape)} does not match data shape {tuple(t.shape)}")
+    nbands = 1 if t.dim() == 2 else t.shape[0]
+    n = z.numel()
+    if out is None:
+        out = torch.empty_like(t)
+    _lib.check(_lib.load().b200_sunz_reduce(t.data_ptr(), z.data_ptr(), out.data_ptr(), nbands, n, n, float(limit),
+                                            float(max_sza), float(strength), _lib.stream_ptr(torch)))
+    return out.cpu().numpy() if was_numpy else out
+
+
+class SunZenithReducer(_SunZenithCorrectorBase):
+    """Reduce the signal at large sun zenith angles (satpy/modifiers/geometry.py:166-207)."""
+
+    def __init__(self, correction_limit=80., max_sza=90, strength=1.3, **kwargs):
+        self.correction_limit = correction_limit
+        self.strength = strength
+        super().__init__(max_sza=max_sza, **kwargs)
+        if self.max_sza is None:
+            raise ValueError("`max_sza` must be defined when using the SunZenithReducer.")
+
+    def __call__(self, projectables, optional_datasets=None, **info):
+        optional = [d for d in (optional_datasets or []) if d is not None]
+        arrays = list(projectables) + list(optional)
+        self._check_areas(arrays)
+        vis = arrays[0]
+        if vis.attrs.get("sunz_corrected"):
+            return vis
+        torch = _lib.require_cuda()
+        if len(arrays) < 2:
+            cz = cos_sza(vis.attrs["area"], vis.attrs["start_time"], lonlat_f32=True, device=True)
+            cz = torch.where(cz >= float(self.max_sza_cos), cz, torch.full_like(cz, float("nan")))
+        else:
+            z = payload(arrays[1])
+            z = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z))
+            cz = torch.cos(torch.deg2rad(z.to("cuda")))
+        sunz = torch.rad2deg(torch.arccos(cz)).to(torch.float32)   # geometry.py:201
+        res = sunz_reduce(payload(vis), sunz, limit=self.correction_limit, max_sza=self.max_sza, strength=self.strength)
+        proj = rewrap(vis, res, attrs=dict(vis.attrs))
+        self.apply_modifier_info(vis, proj)
+        return proj

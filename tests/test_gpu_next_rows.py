@@ -1,0 +1,125 @@
+""""Next" rows of SURVEY.md section 8f on the device: AHI / SEVIRI / VIIRS calibration and SunZenithReducer, against the
+reference's golden vectors and the oracle.  Run with ``-m gpu``."""
+import datetime as dt
+
+import numpy as np
+import pytest
+
+from oracle import calibration as ocal
+from oracle import solar as osolar
+from satpy_b200 import AreaDefinition, DataArrayLite
+from satpy_b200.modifiers import SunZenithReducer, sunz_reduce
+from satpy_b200.readers import AHICalibration, SEVIRICalibration, calibrate_ahi, calibrate_seviri, scale_viirs
+
+from .test_oracle_golden import (SEV_IR108_MET10, _SEV_COUNTS, _SEV_RAD, _SEV_TBS1, _SEV_TBS2, _SEV_VIS_RAD,
+                                 _SEV_VIS_REFL)
+
+pytestmark = pytest.mark.gpu
+
+AHI_KW = dict(gain_count2rad_conversion=-0.0037, offset_count2rad_conversion=15.20, coeff_rad2albedo_conversion=0.0019255,
+              central_wave_length=10.4073, speed_of_light=299792458.0, planck_constant=6.62606957e-34,
+              boltzmann_constant=1.3806488e-23, c0_rad2tb_conversion=-0.116127314574, c1_rad2tb_conversion=1.00099153832,
+              c2_rad2tb_conversion=-1.76961091571e-06)
+AHI_ORACLE_KW = dict(gain=-0.0037, offset=15.20, coeff_rad2albedo=0.0019255, central_wave_length=10.4073,
+                     speed_of_light=299792458.0, planck_constant=6.62606957e-34, boltzmann_constant=1.3806488e-23,
+                     c0=-0.116127314574, c1=1.00099153832, c2=-1.76961091571e-06)
+
+
+def test_ahi_golden_vectors():
+    """satpy/tests/reader_tests/test_ahi_hsd.py:455-506."""
+    counts = np.array([[0, 1000], [2000, 5000]], dtype=np.uint16)
+    cal = AHICalibration(bt_in_float64=False, **AHI_KW)   # the fixture passes Python floats: float32 arithmetic
+    assert calibrate_ahi(123, cal, "counts") == 123
+    rad = calibrate_ahi(counts, cal, "radiance")
+    assert rad.dtype == np.float32 and np.allclose(rad, np.array([[15.2, 11.5], [7.8, -3.3]]))
+    bt = calibrate_ahi(counts, cal, "brightness_temperature")
+    np.testing.assert_allclose(bt, np.array([[330.978979, 310.524688], [285.845017, np.nan]]), rtol=2e-7)
+    refl = calibrate_ahi(counts, cal, "reflectance")
+    assert np.allclose(refl, np.array([[2.92676, 2.214325], [1.50189, 0.]]))
+
+
+@pytest.mark.parametrize("n", [0, 7, 8, 9, 1 << 20])
+@pytest.mark.parametrize("f64", [False, True])
+def test_ahi_matches_oracle(n, f64):
+    rng = np.random.default_rng(n + 3)
+    counts = rng.integers(0, 2048, size=n, dtype=np.uint16)
+    counts[rng.random(n) < 0.01] = 65535
+    counts[rng.random(n) < 0.01] = 65534
+    cal = AHICalibration(count_value_outside_scan_pixels=65535, count_value_error_pixels=65534, bt_in_float64=f64, **AHI_KW)
+    okw = dict(AHI_ORACLE_KW, count_outside_scan=65535, count_error=65534)
+    if f64:  # numpy float64 header scalars, as read from a real file
+        okw.update({k: np.float64(v) for k, v in okw.items() if k in ("central_wave_length", "speed_of_light",
+                    "planck_constant", "boltzmann_constant", "c0", "c1", "c2")})
+    for calib in ("radiance", "reflectance"):
+        np.testing.assert_array_equal(calibrate_ahi(counts, cal, calib), ocal.ahi_calibrate(counts, calib, **okw))
+    bt = calibrate_ahi(counts, cal, "brightness_temperature")
+    ref = ocal.ahi_calibrate(counts, "brightness_temperature", **okw)
+    np.testing.assert_allclose(bt, ref.astype(np.float32), rtol=1e-5, equal_nan=True)
+
+
+def test_seviri_golden_vectors():
+    """satpy/tests/reader_tests/test_seviri_l1b_calibration.py:29-149 (Meteosat-10, IR_108 and VIS008)."""
+    c = SEV_IR108_MET10
+    cal = SEVIRICalibration(gain=0.20503567620766011, offset=-10.456819486590666, wavenumber=c["wavenumber"],
+                            alpha=c["alpha"], beta=c["beta"], btfit=c["btfit"])
+    rad = calibrate_seviri(_SEV_COUNTS, cal, "radiance")
+    assert rad.dtype == np.float32
+    np.testing.assert_allclose(rad, _SEV_RAD, rtol=1e-5)
+    np.testing.assert_allclose(calibrate_seviri(_SEV_COUNTS, cal, "brightness_temperature", "spectral"), _SEV_TBS1, rtol=1e-5)
+    np.testing.assert_allclose(calibrate_seviri(_SEV_COUNTS, cal, "brightness_temperature", "effective"), _SEV_TBS2, rtol=1e-5)
+    with pytest.raises(ValueError, match="No calibration coefficients"):
+        calibrate_seviri(_SEV_COUNTS, cal, "brightness_temperature", "not_processed")
+    # VIS008: feed radiances through gain 1 / offset 0
+    vis = SEVIRICalibration(gain=1.0, offset=0.0, solar_irradiance=73.1807, scan_time=dt.datetime(2020, 8, 15, 13, 0, 40))
+    np.testing.assert_allclose(calibrate_seviri(_SEV_VIS_RAD, vis, "reflectance"), _SEV_VIS_REFL, rtol=1e-5)
+
+
+def test_seviri_matches_oracle_uint16():
+    rng = np.random.default_rng(8)
+    counts = rng.integers(0, 1024, size=(300, 333), dtype=np.uint16)
+    c = SEV_IR108_MET10
+    cal = SEVIRICalibration(gain=0.2050356762, offset=-10.4568194866, wavenumber=c["wavenumber"], alpha=c["alpha"],
+                            beta=c["beta"], btfit=c["btfit"])
+    rad = ocal.seviri_radiance(counts, cal.gain, cal.offset)
+    np.testing.assert_array_equal(calibrate_seviri(counts, cal, "radiance"), rad)
+    np.testing.assert_allclose(calibrate_seviri(counts, cal, "brightness_temperature", "effective"),
+                               ocal.seviri_erads2bt(rad, c["wavenumber"], c["alpha"], c["beta"]), rtol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(calibrate_seviri(counts, cal, "brightness_temperature", "spectral"),
+                               ocal.seviri_srads2bt(rad, c["wavenumber"], c["btfit"]), rtol=1e-5, equal_nan=True)
+
+
+def test_viirs_scale_matches_oracle():
+    rng = np.random.default_rng(12)
+    rows_per_gran = [768, 768, 752]
+    data = rng.integers(0, 65536, size=(sum(rows_per_gran), 320), dtype=np.uint16)
+    factors = np.array([2.0e-3, -0.5, 1.9e-3, -0.4, -999.9, -999.9], np.float32)
+    out = scale_viirs(data, factors, rows_per_gran)
+    ref = ocal.viirs_scale(data, factors, rows_per_gran)
+    assert out.dtype == np.float32
+    np.testing.assert_array_equal(out, ref)
+    fdata = rng.uniform(-1200, 300, size=(32, 64)).astype(np.float32)
+    np.testing.assert_array_equal(scale_viirs(fdata, [1.5, 2.0], [32]), ocal.viirs_scale(fdata, [1.5, 2.0], [32]))
+    with pytest.raises(ValueError):
+        scale_viirs(data, factors, [768, 768])
+
+
+def test_sunz_reducer_golden_and_oracle():
+    """satpy/tests/test_modifiers.py:186-220."""
+    area = AreaDefinition("test", "test", "test", {"proj": "merc"}, 2, 2, (-2000, -2000, 2000, 2000))
+    sza = np.rad2deg(np.arccos(np.array([[0.0149581333, 0.0146694376], [0.0150812684, 0.0147925727]]))).astype(np.float32)
+    ds = DataArrayLite(np.ones((2, 2), np.float32), ("y", "x"), {"area": area, "start_time": dt.datetime(2018, 1, 1, 18),
+                                                                "name": "test_vis", "modifiers": tuple()})
+    sz = DataArrayLite(sza, ("y", "x"), {"area": area})
+    res = SunZenithReducer(name="sza_reduction_test_default", modifiers=tuple())((ds, sz))
+    np.testing.assert_allclose(res.values, np.array([[0.02916261, 0.02839063], [0.02949383, 0.02871911]], np.float32), rtol=2e-5)
+    res = SunZenithReducer(name="custom", modifiers=tuple(), correction_limit=70, max_sza=95, strength=3.0)((ds, sz))
+    np.testing.assert_allclose(res.values, np.array([[0.01041319, 0.01030033], [0.01046164, 0.01034834]], np.float32), rtol=2e-5)
+    with pytest.raises(ValueError, match="`max_sza` must be defined"):
+        SunZenithReducer(name="x", max_sza=None)
+    rng = np.random.default_rng(1)
+    data = rng.uniform(0, 100, (2, 200, 300)).astype(np.float32)
+    z = rng.uniform(0, 100, (200, 300)).astype(np.float32)
+    z[0, :5] = np.nan
+    out = sunz_reduce(data, z, limit=55.0, max_sza=90.0, strength=1.5)
+    ref = osolar.sunzen_reduction(data, z, limit=55., max_sza=90., strength=1.5).astype(np.float32)
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)

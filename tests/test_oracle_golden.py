@@ -202,3 +202,73 @@ def test_solar_scalars_host_copy_agrees_with_oracle():
         a, b = solar_scalars(t), osolar.solar_scalars(t)
         for u, v in zip(a, b):
             assert math.isclose(u, v, rel_tol=0, abs_tol=1e-12)
+
+
+# -------------------------------------------------------- "next" rows: AHI / SEVIRI calibration
+def test_ahi_calibrate_golden():
+    """satpy/tests/reader_tests/test_ahi_hsd.py:455-506 (default in-file calibration)."""
+    counts = np.array([[0, 1000], [2000, 5000]], dtype=np.uint16)
+    kw = dict(gain=-0.0037, offset=15.20, coeff_rad2albedo=0.0019255, central_wave_length=10.4073,
+              speed_of_light=299792458.0, planck_constant=6.62606957e-34, boltzmann_constant=1.3806488e-23,
+              c0=-0.116127314574, c1=1.00099153832, c2=-1.76961091571e-06)
+    rad = ocal.ahi_calibrate(counts, "radiance", **kw)
+    assert rad.dtype == np.float32
+    assert np.allclose(rad, np.array([[15.2, 11.5], [7.8, -3.3]]))
+    bt = ocal.ahi_calibrate(counts, "brightness_temperature", **kw)
+    np.testing.assert_allclose(bt, np.array([[330.978979, 310.524688], [285.845017, np.nan]]))
+    refl = ocal.ahi_calibrate(counts, "reflectance", **kw)
+    assert np.allclose(refl, np.array([[2.92676, 2.214325], [1.50189, 0.]]))
+
+
+_SEV_COUNTS = np.array([[377., 377., 377., 376., 375.], [376., 375., 376., 374., 374.], [374., 373., 373., 374., 374.],
+                        [347., 345., 345., 348., 347.], [306., 306., 307., 307., 308.]], dtype=np.float32)
+_SEV_RAD = np.array([[66.84162903, 66.84162903, 66.84162903, 66.63659668, 66.4315567],
+                     [66.63659668, 66.4315567, 66.63659668, 66.22652435, 66.22652435],
+                     [66.22652435, 66.02148438, 66.02148438, 66.22652435, 66.22652435],
+                     [60.69055939, 60.28048706, 60.28048706, 60.89559937, 60.69055939],
+                     [52.28409576, 52.28409576, 52.48912811, 52.48912811, 52.69416809]], dtype=np.float32)
+_SEV_TBS1 = np.array([[269.29684448, 269.29684448, 269.29684448, 269.13296509, 268.96871948],
+                      [269.13296509, 268.96871948, 269.13296509, 268.80422974, 268.80422974],
+                      [268.80422974, 268.63937378, 268.63937378, 268.80422974, 268.80422974],
+                      [264.23751831, 263.88912964, 263.88912964, 264.41116333, 264.23751831],
+                      [256.77682495, 256.77682495, 256.96743774, 256.96743774, 257.15756226]], dtype=np.float32)
+_SEV_TBS2 = np.array([[268.94519043, 268.94519043, 268.94519043, 268.77984619, 268.61422729],
+                      [268.77984619, 268.61422729, 268.77984619, 268.44830322, 268.44830322],
+                      [268.44830322, 268.28204346, 268.28204346, 268.44830322, 268.44830322],
+                      [263.84396362, 263.49285889, 263.49285889, 264.01898193, 263.84396362],
+                      [256.32858276, 256.32858276, 256.52044678, 256.52044678, 256.71188354]], dtype=np.float32)
+_SEV_VIS_RAD = np.array([[0.62234485, 0.59405649, 0.59405649, 0.59405649, 0.59405649],
+                         [0.59405649, 0.62234485, 0.62234485, 0.59405649, 0.62234485],
+                         [0.76378691, 0.79207528, 0.79207528, 0.76378691, 0.79207528],
+                         [3.30974245, 3.33803129, 3.33803129, 3.25316572, 3.47947311],
+                         [7.52471399, 7.83588648, 8.2602129, 8.57138538, 8.99571133]], dtype=np.float32)
+_SEV_VIS_REFL = np.array([[2.739768, 2.615233, 2.615233, 2.615233, 2.615233], [2.615233, 2.739768, 2.739768, 2.615233, 2.739768],
+                          [3.362442, 3.486977, 3.486977, 3.362442, 3.486977],
+                          [14.570578, 14.695117, 14.695117, 14.321507, 15.317789],
+                          [33.126278, 34.49616, 36.364185, 37.73407, 39.60209]], dtype=np.float32)
+SEV_IR108_MET10 = dict(wavenumber=929.842, alpha=0.9983, beta=0.6084, btfit=(-0.00007392770, 1.032889800, -3.296740))
+
+
+def test_seviri_calibration_golden():
+    """satpy/tests/reader_tests/test_seviri_l1b_calibration.py:29-100,113-149 (Meteosat-10 IR_108, VIS008)."""
+    rad = ocal.seviri_radiance(_SEV_COUNTS, 0.20503567620766011, -10.456819486590666)
+    assert rad.dtype == np.float32
+    np.testing.assert_allclose(rad, _SEV_RAD, rtol=1e-5)
+    c = SEV_IR108_MET10
+    tb1 = ocal.seviri_srads2bt(_SEV_RAD, c["wavenumber"], c["btfit"])
+    np.testing.assert_allclose(tb1, _SEV_TBS1, rtol=1e-5)
+    assert tb1.dtype == np.float32
+    tb2 = ocal.seviri_erads2bt(_SEV_RAD, c["wavenumber"], c["alpha"], c["beta"])
+    np.testing.assert_allclose(tb2, _SEV_TBS2, rtol=1e-5)
+    refl = ocal.seviri_vis_calibrate(_SEV_VIS_RAD, 73.1807, dt.datetime(2020, 8, 15, 13, 0, 40))
+    assert refl.dtype == np.float32
+    np.testing.assert_allclose(refl, _SEV_VIS_REFL, rtol=1e-5)
+
+
+def test_viirs_scale():
+    """Per-granule factors and fill masking (satpy/readers/core/viirs_atms_sdr.py:197-214,328-361)."""
+    data = np.array([[0, 100], [65527, 65528], [200, 65535], [5, 6]], dtype=np.uint16)
+    out = ocal.viirs_scale(data, [2.0, 1.0, 0.5, -1.0], rows_per_granule=[2, 2])
+    np.testing.assert_array_equal(out, np.array([[1, 201], [131055, np.nan], [99, np.nan], [1.5, 2.0]], np.float32))
+    out = ocal.viirs_scale(np.array([[1.0, -999.0], [-999.5, 3.0]], np.float32), [-999.9, 0.0, 1.0, 1.0], [1, 1])
+    assert np.isnan(out[0]).all() and np.isnan(out[1, 0]) and out[1, 1] == 4.0
