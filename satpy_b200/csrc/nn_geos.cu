@@ -194,9 +194,9 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
         // Where the lattice is locally a parallelogram lattice (it is, except next to the limb), most points of that
         // disc can be ruled out without loading them: with e_c, e_r the 3-D steps along a row / a column, the
         // distance to lattice point (i, j) is |h|^2 + Q(i - fx, j - fy), Q the quadratic form of the Gram matrix.
-        // Only points with Q < (1.5 * best + 50 m)^2 are examined.  The model is used when all four block pixels are
+        // Only points with Q < (1.25 * best + 30 m)^2 are examined.  The model is used when all four block pixels are
         // valid and the fourth one lies within 2 % of a pixel of where the other three predict it (the measured
-        // second-order term; over the few pixels of the disc it stays far inside the 50 % + 50 m margin).
+        // second-order term; over the few pixels of the disc it stays inside the 25 % + 30 m margin).
         bool model = G.prune && (p00.x < inf) && (p01.x < inf) && (p10.x < inf) && (p11.x < inf);
         float gcc = 0.f, gcr = 0.f, grr = 0.f, det = 0.f, ecx = 0.f, ecy = 0.f, ecz = 0.f, erx = 0.f, ery = 0.f, erz = 0.f;
         if (model) {
@@ -214,7 +214,7 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
             const float bc = d0x * ecx + d0y * ecy + d0z * ecz, br = d0x * erx + d0y * ery + d0z * erz;
             const float inv_det = 1.0f / det;
             const float fx = (bc * grr - br * gcr) * inv_det, fy = (br * gcc - bc * gcr) * inv_det;  // model position
-            const float B = 1.5f * bd + 50.0f, B2 = B * B;
+            const float B = 1.25f * bd + 30.0f, B2 = B * B;
             const float hb = B * sqrtf(gcc * inv_det);
             const int jlo = max(rlo, r0 + (int)ceilf(fy - hb)), jhi = min(rhi, r0 + (int)floorf(fy + hb));
             const float inv_gcc = 1.0f / gcc;
@@ -331,7 +331,7 @@ nn_seg_cmax_kernel(const TgtCol *__restrict__ cols, int W, int nseg, float *__re
 // rectilinear targets: one work item = 256 consecutive columns of one row, tables instead of trigonometry; items are
 // handed out in order through an atomic counter (chunks of GEOS_CHUNK consecutive segments).
 // FUSED1: the hot configuration -- fused gather of one float32 band, no index outputs.
-#define GEOS_CHUNK 8
+#define GEOS_CHUNK 16
 template <bool FUSED1>
 __global__ void __launch_bounds__(256, 4)
 nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long long *__restrict__ queue,
@@ -339,6 +339,7 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
     const int W = (int)Q.dst.width;
     const int nseg = (W + 255) >> 8;
     const long long items = (long long)Q.dst.nrows * nseg;
+    const int lane = threadIdx.x & 31;
     __shared__ int s_row, s_seg, s_count;
     for (;;) {
         if (threadIdx.x == 0) {
@@ -356,20 +357,34 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
         int r = s_row, seg = s_seg;
         __syncthreads();
         if (count == 0) break;
+        // Which items of the chunk can see the satellite at all?  Lane k looks at item k, so the (row, segment) table
+        // reads of the whole chunk are in flight together instead of one dependent read per item.
+        bool vis = false;
+        if (lane < count) {
+            int rk = r, sk = seg + lane;
+            while (sk >= nseg) {
+                sk -= nseg;
+                ++rk;
+            }
+            const TgtRow *Rk = Q.rows + rk;
+            vis = Rk->valid && (Rk->rc * __ldg(seg_cmax + sk) >= Q.G.vis_min);
+        }
+        const unsigned vmask = __ballot_sync(0xffffffffu, vis);
+        int64_t row_base = (int64_t)r * W;
         for (int k = 0; k < count; ++k, ++seg) {
             if (seg == nseg) {
                 seg = 0;
                 ++r;
+                row_base += W;
             }
-            const TgtRow R = Q.rows[r];
             const int col = seg * 256 + (int)threadIdx.x;
-            const int64_t i = (int64_t)r * W + col;
-            if (!R.valid || !(R.rc * __ldg(seg_cmax + seg) >= Q.G.vis_min)) {
+            const int64_t i = row_base + col;
+            if (!((vmask >> k) & 1u)) {
                 // nothing of this segment can see the satellite: every pixel is a miss
                 if (FUSED1) {
                     if (threadIdx.x < 64) {  // two warps write the 1 KB of the segment, the others move on
                         const int n = min(256, W - seg * 256);
-                        float *dst = Q.O.out + (int64_t)r * W + seg * 256;
+                        float *dst = Q.O.out + row_base + seg * 256;
                         // rows are 8-byte aligned at worst (even widths): peel to a 16-byte boundary
                         const int head = (int)(((16 - (((uintptr_t)dst) & 15)) & 15) >> 2);
                         const int j = head + (int)threadIdx.x * 4;
@@ -378,11 +393,12 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
                         if ((int)threadIdx.x < head && (int)threadIdx.x < n) st_stream_f1(dst + threadIdx.x, Q.O.fill);
                     }
                 } else if (col < W) {
-                    b200_nn_emit(Q.O, Q.G.prefix, i, -1, R.valid && Q.cols[col].valid);
+                    b200_nn_emit(Q.O, Q.G.prefix, i, -1, Q.rows[r].valid && Q.cols[col].valid);
                 }
                 continue;
             }
             if (col >= W) continue;
+            const TgtRow R = Q.rows[r];
             const TgtCol Cc = Q.cols[col];
             const bool ok = Cc.valid;
             long long raw = -1;
