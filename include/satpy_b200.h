@@ -245,6 +245,17 @@ int b200_nn_query_gather_f32(const b200_nn_grid_t *grid, const b200_geo_t *dst, 
 int b200_nn_compressed_to_raw(const uint8_t *valid_input, int64_t n_src, const int32_t *index_array,
                               int32_t *gather_index, int64_t n_out, void *stream);
 
+/* ------------------------------------------------------- native resampler, SimulatedGreen
+ * NativeResampler (resample/native.py:41-159): repeat every pixel fy x fx times (any dtype of elem_size
+ * bytes, nbands leading images) or np.nanmean over fy x fx blocks (2-D float32).
+ * SimulatedGreen (composites/abi.py:56-61): c01 * f1 + c02 * f2 + c03 * f3 in float32. */
+int b200_native_replicate(const void *data, void *out, int64_t nbands, int64_t rows, int64_t cols, int32_t fy,
+                          int32_t fx, int32_t elem_size, void *stream);
+int b200_native_aggregate_f32(const float *data, float *out, int64_t out_rows, int64_t out_cols, int32_t fy,
+                              int32_t fx, void *stream);
+int b200_simulated_green(const float *c01, const float *c02, const float *c03, float *out, int64_t n, float f1,
+                         float f2, float f3, void *stream);
+
 /* ---------------------------------------------------------------- bilinear
  * Replaces pyresample XArrayBilinearResampler.get_bil_info / get_sample_from_bil_info as driven by
  * BilinearResampler.precompute / .compute (resample/kdtree.py:216-242, 281-293).  PARITY UNPINNED in the

@@ -105,6 +105,9 @@ SIGNATURES = {
     "b200_nn_query_gather_f32": (C.c_int, [_P, _GEO, C.c_double, _P, _P, C.c_int32, C.c_int64, C.c_int64,
                                            C.c_float, _P]),
     "b200_nn_compressed_to_raw": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P]),
+    "b200_native_replicate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "b200_native_aggregate_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "b200_simulated_green": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _P]),
     "b200_bil_info": (C.c_int, [_P, _P, _GEO, C.c_double, C.c_int32, _P, _P, _P, _P, _P]),
     "b200_bil_sample_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_float, _P]),
     "b200_ll2cr": (C.c_int, [_GEO, _GEO, _P, _P, C.POINTER(C.c_int64), _P]),

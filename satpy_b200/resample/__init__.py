@@ -7,6 +7,7 @@ listed in ``satpy.resample.base.RESAMPLER_MODULES`` (satpy/resample/base.py:77-1
 """
 from .bilinear import B200BilinearResampler  # noqa: F401
 from .ewa import B200EWAResampler  # noqa: F401
+from .native import B200NativeResampler  # noqa: F401
 from .nearest import NN_COORDINATES, B200NearestResampler  # noqa: F401
 
 
@@ -16,4 +17,5 @@ def get_resampler_classes():
         "b200_nearest": B200NearestResampler,
         "b200_bilinear": B200BilinearResampler,
         "b200_ewa": B200EWAResampler,
+        "b200_native": B200NativeResampler,
     }

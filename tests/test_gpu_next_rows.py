@@ -123,3 +123,48 @@ def test_sunz_reducer_golden_and_oracle():
     out = sunz_reduce(data, z, limit=55.0, max_sza=90.0, strength=1.5)
     ref = osolar.sunzen_reduction(data, z, limit=55., max_sza=90., strength=1.5).astype(np.float32)
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_native_resampler_replicate_and_aggregate():
+    """satpy/resample/native.py:41-159 (cf. satpy/tests/test_resample.py TestNativeResampler: expand, reduce, errors)."""
+    from satpy_b200.resample import B200NativeResampler
+    rng = np.random.default_rng(5)
+    small = AreaDefinition("s", "s", "s", {"proj": "merc"}, 50, 40, (-2000, -2000, 2000, 2000))
+    big = AreaDefinition("b", "b", "b", {"proj": "merc"}, 100, 120, (-2000, -2000, 2000, 2000))
+    for dtype in (np.float32, np.int16, np.uint8, np.float64):
+        data = (rng.uniform(0, 200, (3, 40, 50))).astype(dtype)
+        out = B200NativeResampler(small, big).resample(data)
+        assert out.dtype == dtype
+        np.testing.assert_array_equal(out, np.repeat(np.repeat(data, 3, axis=1), 2, axis=2))
+    d2 = rng.uniform(0, 1, (120, 100)).astype(np.float32)
+    d2[rng.random(d2.shape) < 0.2] = np.nan
+    d2[:3, :2] = np.nan   # an all-NaN block
+    ds = DataArrayLite(d2, ("y", "x"), {"area": big})
+    res = B200NativeResampler(big, [big, small]).compute(ds, expand=False)
+    assert res.attrs["area"] is small
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exp = np.nanmean(d2.reshape(40, 3, 50, 2), axis=(1, 3))
+    np.testing.assert_allclose(res.values, exp, rtol=1e-6, equal_nan=True)
+    np.testing.assert_array_equal(B200NativeResampler(small, small).resample(d2[:40, :50]), d2[:40, :50])
+    odd = AreaDefinition("o", "o", "o", {"proj": "merc"}, 75, 60, (-2000, -2000, 2000, 2000))
+    with pytest.raises(ValueError, match="whole number"):
+        B200NativeResampler(small, odd).resample(d2[:40, :50])
+    with pytest.raises(ValueError, match="more than 2 dimensions"):
+        B200NativeResampler(big, small).resample(np.zeros((2, 120, 100), np.float32))
+
+
+def test_simulated_green():
+    """satpy/composites/abi.py:56-61."""
+    from satpy_b200.composites import SimulatedGreen
+    rng = np.random.default_rng(6)
+    c = [rng.uniform(0, 120, (300, 500)).astype(np.float32) for _ in range(3)]
+    c[1][5, 5] = np.nan
+    area = AreaDefinition("s", "s", "s", {"proj": "merc"}, 500, 300, (-2000, -2000, 2000, 2000))
+    ds = [DataArrayLite(a, ("y", "x"), {"area": area, "name": n}) for a, n in zip(c, ("C01", "C02", "C03"))]
+    res = SimulatedGreen("green", fractions=(0.465, 0.465, 0.07))(ds)
+    exp = c[0] * 0.465 + c[1] * 0.465 + c[2] * 0.07
+    assert exp.dtype == np.float32 and res.dtype == np.float32
+    np.testing.assert_array_equal(res.values, exp)
+    assert res.attrs["name"] == "green" and res.attrs["area"] is area
