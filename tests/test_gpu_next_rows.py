@@ -168,3 +168,45 @@ def test_simulated_green():
     assert exp.dtype == np.float32 and res.dtype == np.float32
     np.testing.assert_array_equal(res.values, exp)
     assert res.attrs["name"] == "green" and res.attrs["area"] is area
+
+
+def test_config2_chain_matches_oracle():
+    """BASELINE.json configs[1] in miniature: C01-C03 counts -> reflectance -> sunz (one fused launch for the three
+    bands) -> ONE neighbour search -> gather x3 -> SimulatedGreen, against the oracle chain."""
+    import ctypes as C
+    import torch
+    from oracle import nearest as onn
+    from oracle import reference_pipeline as rp
+    from oracle.projections import Area as OArea
+    from satpy_b200 import _lib, demo
+    from satpy_b200.composites import SimulatedGreen
+    from satpy_b200.modifiers.geometry import _sunz_struct
+    from satpy_b200.resample import B200NearestResampler
+    s, d = 500 / 5424, 800 / 9050
+    src, dst = demo.make_area("goes_east_abi_f_2km", s), demo.make_area("goes_east_eqc_2km", d)
+    o_src, o_dst = OArea(*demo.area_params("goes_east_abi_f_2km", s)), OArea(*demo.area_params("goes_east_eqc_2km", d))
+    bands = ("C01", "C02", "C03")
+    counts = [demo.abi_counts(src.shape, seed=2 + i, band=b) for i, b in enumerate(bands)]
+    cdev = [torch.from_numpy(c).cuda() for c in counts]
+    refl = torch.empty((3,) + src.shape, dtype=torch.float32, device="cuda")
+    cals = (_lib.AbiCalStruct * 3)(*[demo.abi_calibration(b).struct("reflectance") for b in bands])
+    g = src.geo_struct()
+    sz = _sunz_struct(demo.START_TIME, 88.0, 95.0, True, 0)
+    _lib.check(_lib.load().b200_abi_vis_sunz((C.c_void_p * 3)(*[t.data_ptr() for t in cdev]),
+                                             (C.c_void_p * 3)(*[refl[i].data_ptr() for i in range(3)]), cals, 3,
+                                             C.byref(g), C.byref(sz), _lib.stream_ptr(torch)))
+    radius = 2.5 * 2004.0 / s
+    r = B200NearestResampler(src, dst)
+    out = r.resample(refl, radius_of_influence=radius)          # one search, three gathers
+    green = SimulatedGreen("green")([out[0], out[1], out[2]]).cpu().numpy()
+    # oracle chain
+    ref_bands = np.stack([rp.abi_sunz(c, demo.ABI_BANDS[b], o_src, demo.START_TIME) for c, b in zip(counts, bands)])
+    slon, slat = o_src.get_lonlats()
+    dlon, dlat = o_dst.get_lonlats()
+    vin, vout, idx = onn.get_neighbour_info(slon, slat, dlon, dlat, radius)
+    ref = onn.get_sample_from_neighbour_info(ref_bands, vin, idx, np.float32(np.nan))
+    ref_green = ref[0] * 0.465 + ref[1] * 0.465 + ref[2] * 0.07
+    assert (np.isnan(green) != np.isnan(ref_green)).mean() < 1e-5
+    ok = ~np.isnan(green) & ~np.isnan(ref_green)
+    err = np.abs(green[ok] - ref_green[ok]) / np.maximum(np.abs(ref_green[ok]), 1e-3)
+    assert ok.mean() > 0.3 and (err > 1e-5).mean() < 2e-3   # equidistant ties may pick the twin pixel
