@@ -23,6 +23,7 @@
 // Rectilinear targets are processed through a dynamic work queue so that all blocks sweep one compact front of
 // target rows: the source records they share then stay in L2 although per-item cost varies 10x (on/off disk).
 #include "nn_common.cuh"
+#include "b200_geos_fast.cuh"
 
 #define GEOS_BOUND_FACTOR 0.975
 #define GEOS_POS_ERR 0.02f
@@ -533,6 +534,7 @@ struct BilArg {
 struct SrcProjArg {
     b200_geo_t src;
     b200_proj_t dst_proj;
+    GeosFast fast;
 };
 
 __global__ void __launch_bounds__(256)
@@ -547,7 +549,10 @@ bil_source_xy_kernel(const __grid_constant__ SrcProjArg A, const uint8_t *__rest
         if (valid_input[i]) {
             int64_t r = i / W;
             double lon, lat;
-            b200_geo_lonlat(A.src, A.src.row0 + r, i - r * W, lon, lat);
+            if (A.fast.enabled)
+                geos_fast_lonlat(A.fast, A.src.row0 + r, i - r * W, lon, lat);
+            else
+                b200_geo_lonlat(A.src, A.src.row0 + r, i - r * W, lon, lat);
             if (!b200_proj_forward(A.dst_proj, lon, lat, x, y)) x = y = __longlong_as_double(0x7ff0000000000000LL);
         }
         in_xy[i] = make_double2(x, y);
@@ -647,7 +652,8 @@ __global__ void __launch_bounds__(128) bil_info_kernel(const __grid_constant__ B
         }
         const float reach = Q.w_max + 1.0f;
         if (have_pos && fc > -reach && fc < (float)G.W + reach && fr > -reach && fr < (float)G.H + reach) {
-            float w = 4.0f;
+            float w = 2.0f;  // ~13 lattice points: enough for the four quadrant pixels of a well-sampled target
+            int n_examined = 0;
             for (;;) {
                 if (w > Q.w_max) w = Q.w_max;
                 const double bound = (double)(w - GEOS_POS_ERR) / (double)G.inv_step;  // metres: complete up to here
@@ -659,6 +665,7 @@ __global__ void __launch_bounds__(128) bil_info_kernel(const __grid_constant__ B
                 nd = inf;
                 ni = -1;
                 n_found = 0;
+                n_examined = 0;
                 int n_in_bound = 0;
                 const float w2 = w * w;
                 const int rlo = max(0, (int)ceilf(fr - w)), rhi = min(G.H - 1, (int)floorf(fr + w));
@@ -673,6 +680,7 @@ __global__ void __launch_bounds__(128) bil_info_kernel(const __grid_constant__ B
                         const double2 *p = reinterpret_cast<const double2 *>(G.pts + idx);
                         const double2 a = __ldg(p), b = __ldg(p + 1);
                         const double d2 = b200_nn_d2(a.x, a.y, b.x, tx, ty, tz);
+                        ++n_examined;
                         if (!(d2 < G.r2)) continue;  // invalid pixel (NaN) or outside the radius
                         ++n_found;
                         if (d2 <= bound2) ++n_in_bound;
@@ -695,7 +703,7 @@ __global__ void __launch_bounds__(128) bil_info_kernel(const __grid_constant__ B
             }
             // rank of each quadrant's pixel among all neighbours (nearest first); beyond `neighbours` it is not seen
             int rank[4] = {0, 0, 0, 0};
-            {
+            if (n_examined >= Q.neighbours) {  // with fewer points examined no rank can reach `neighbours`
                 const float w2 = w * w;
                 const int rlo = max(0, (int)ceilf(fr - w)), rhi = min(G.H - 1, (int)floorf(fr + w));
                 for (int rr_ = rlo; rr_ <= rhi; ++rr_) {
@@ -830,7 +838,9 @@ extern "C" int b200_bil_info(const b200_nn_grid_t *grid, const uint8_t *valid_in
         SrcProjArg A;
         A.src = src;
         A.dst_proj = dst->area.proj;
+        b200_geos_fast_prepare(&src, &A.fast, st);
         bil_source_xy_kernel<<<b200_grid_for(grid->n_src, 256, 8), 256, 0, st>>>(A, valid_input, in_xy);
+        b200_geos_fast_release(&A.fast, st);
         bil_first_valid_kernel<<<b200_grid_for(grid->n_src, 256, 8), 256, 0, st>>>(valid_input, grid->n_src, d_first);
         e = cudaMemcpyAsync(&h_first, d_first, sizeof(int), cudaMemcpyDeviceToHost, st);
     }
