@@ -174,6 +174,13 @@ int b200_sunz_correct(const float *data, float *out, int32_t nbands, int64_t ban
 int b200_sunz_correct_sza(const float *data, const float *sza_deg, float *out, int32_t nbands,
                           int64_t band_stride, int64_t n, const b200_sunz_t *sz, void *stream);
 
+/* float64 data (the reference's tests run both dtypes, tests/test_modifiers.py:116-176): lon/lat are then
+ * NOT rounded to float32 (angles.py:427-429 casts them to the data dtype) and the product is float64. */
+int b200_sunz_correct_f64(const double *data, double *out, int32_t nbands, int64_t band_stride,
+                          const b200_geo_t *geo, const b200_sunz_t *sz, void *stream);
+int b200_sunz_correct_sza_f64(const double *data, const double *sza_deg, double *out, int32_t nbands,
+                              int64_t band_stride, int64_t n, const b200_sunz_t *sz, void *stream);
+
 /* SunZenithReducer (modifiers/geometry.py:166-207 -> angles.py:594-624): out = data * reduction(sza). */
 int b200_sunz_reduce(const float *data, const float *sunz_deg, float *out, int32_t nbands, int64_t band_stride,
                      int64_t n, float limit_deg, float max_sza_deg, float strength, void *stream);

@@ -92,6 +92,8 @@ SIGNATURES = {
     "b200_sunz_reduce": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, _P]),
     "b200_cos_sza": (C.c_int, [_GEO, C.POINTER(SunzStruct), _P, _P]),
     "b200_sunz_correct": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _GEO, C.POINTER(SunzStruct), _P]),
+    "b200_sunz_correct_f64": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _GEO, C.POINTER(SunzStruct), _P]),
+    "b200_sunz_correct_sza_f64": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.POINTER(SunzStruct), _P]),
     "b200_sunz_correct_sza": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.POINTER(SunzStruct), _P]),
     "b200_abi_vis_sunz": (C.c_int, [C.POINTER(_P), C.POINTER(_P), C.POINTER(AbiCalStruct), C.c_int32, _GEO,
                                     C.POINTER(SunzStruct), _P]),

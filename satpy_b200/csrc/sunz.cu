@@ -53,6 +53,19 @@ __device__ __forceinline__ double b200_li_shibata(double cz) {
     return 24.35 / (2.0 * cz + sqrt(498.5225 * cz * cz + 1.0));
 }
 
+// correction factor for float64 data: everything stays float64 (the reference's .astype(data.dtype) is a no-op)
+__device__ __forceinline__ double b200_sunz_corr_d(const SunzDev &S, double cz) {
+    if (S.has_max && !(cz >= S.max_cos)) cz = __longlong_as_double(0x7ff8000000000000LL);
+    if (isnan(cz)) return 0.0;
+    const double base_lim = S.method == 0 ? 1.0 / S.limit_cos : S.li_lim;
+    if (cz > S.limit_cos) return S.method == 0 ? 1.0 / cz : b200_li_shibata(cz);
+    if (!S.has_max) return base_lim;
+    double gf = (acos(cz) - S.limit_rad) / S.span;
+    gf = 1.0 - log(gf + 1.0) / 0.6931471805599453;
+    gf = gf < 0.0 ? 0.0 : gf;
+    return S.method == 0 ? gf / S.limit_cos : gf * S.li_lim;
+}
+
 // correction factor from a float64 cos(sza) (computed-angles branch)
 __device__ __forceinline__ float b200_sunz_corr(const SunzDev &S, double cz) {
     if (S.has_max && !(cz >= S.max_cos)) cz = __longlong_as_double(0x7ff8000000000000LL);
@@ -95,6 +108,43 @@ sunz_correct_kernel(const float *__restrict__ data, float *__restrict__ out, int
         int64_t r = i / W;
         float corr = b200_sunz_corr(S, b200_cos_sza_pixel(S, S.geo.row0 + r, i - r * W));
         for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __fmul_rn(data[b * band_stride + i], corr);
+    }
+}
+
+// float64 data: lon/lat are not rounded (S.lonlat_f32 = 0), the product is float64
+__global__ void __launch_bounds__(256)
+sunz_correct_f64_kernel(const double *__restrict__ data, double *__restrict__ out, int nbands, int64_t band_stride,
+                        const __grid_constant__ SunzDev S) {
+    const int64_t W = S.geo.width;
+    const int64_t n = S.geo.nrows * W;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int64_t r = i / W;
+        double corr = b200_sunz_corr_d(S, b200_cos_sza_pixel(S, S.geo.row0 + r, i - r * W));
+        for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __dmul_rn(data[b * band_stride + i], corr);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sunz_correct_sza_f64_kernel(const double *__restrict__ data, const double *__restrict__ sza, double *__restrict__ out,
+                            int nbands, int64_t band_stride, int64_t n, const __grid_constant__ SunzDev S) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // the provided-SZA branch applies no max_sza mask (geometry.py:64-66): only the fall-off uses max_sza
+        const double cz = cos(sza[i] * B200_DEG2RAD);
+        double corr;
+        if (isnan(cz)) corr = 0.0;
+        else if (cz > S.limit_cos) corr = S.method == 0 ? 1.0 / cz : b200_li_shibata(cz);
+        else {
+            const double base = S.method == 0 ? 1.0 / S.limit_cos : S.li_lim;
+            if (S.has_max) {
+                double gf = (acos(cz) - S.limit_rad) / S.span;
+                gf = 1.0 - log(gf + 1.0) / 0.6931471805599453;
+                gf = gf < 0.0 ? 0.0 : gf;
+                corr = gf * base;
+            } else corr = base;
+        }
+        for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __dmul_rn(data[b * band_stride + i], corr);
     }
 }
 
@@ -216,6 +266,40 @@ extern "C" int b200_sunz_correct(const float *data, float *out, int32_t nbands, 
     sunz_correct_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands,
                                                                                   band_stride, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_sunz_correct_f64(const double *data, double *out, int32_t nbands, int64_t band_stride,
+                                     const b200_geo_t *geo, const b200_sunz_t *sz, void *stream) {
+    SunzDev S;
+    int rc = fill_sunz(S, geo, sz, true);
+    if (rc) return rc;
+    S.lonlat_f32 = 0;  // float64 data: lon/lat keep their float64 values (angles.py:427-429 casts to the DATA dtype)
+    B200_CHECK_ARG(nbands >= 1, "nbands must be >= 1");
+    int64_t n = geo->nrows * geo->width;
+    if (n == 0) return B200_OK;
+    B200_CHECK_ARG(data != nullptr && out != nullptr, "NULL data pointer");
+    B200_CHECK_ARG(nbands == 1 || band_stride >= n, "band stride smaller than one image");
+    rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
+    if (rc) return rc;
+    sunz_correct_f64_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
+    b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_sunz_correct_sza_f64(const double *data, const double *sza_deg, double *out, int32_t nbands,
+                                         int64_t band_stride, int64_t n, const b200_sunz_t *sz, void *stream) {
+    SunzDev S;
+    int rc = fill_sunz(S, nullptr, sz, false);
+    if (rc) return rc;
+    B200_CHECK_ARG(nbands >= 1 && n >= 0, "bad shape");
+    if (n == 0) return B200_OK;
+    B200_CHECK_ARG(data && sza_deg && out, "NULL data pointer");
+    B200_CHECK_ARG(nbands == 1 || band_stride >= n, "band stride smaller than one image");
+    sunz_correct_sza_f64_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, sza_deg, out, nbands,
+                                                                                           band_stride, n, S);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -48,15 +48,16 @@ def _sunz_struct(start_time, limit, max_sza, lonlat_f32, method):
     return s
 
 
-def _to_cuda_f32(torch, data):
+def _to_cuda_f32(torch, data, allow_f64=False):
     was_numpy = not isinstance(data, torch.Tensor)
+    ok = (np.float32, np.float64) if allow_f64 else (np.float32,)
     if was_numpy:
         a = np.ascontiguousarray(data)
-        if a.dtype != np.float32:
-            raise TypeError(f"the device sun-zenith correction works on float32 data, got {a.dtype}")
+        if a.dtype not in ok:
+            raise TypeError(f"the device sun-zenith correction works on float32/float64 data, got {a.dtype}")
         return torch.from_numpy(a).to("cuda", non_blocking=True), True
-    if data.dtype != torch.float32:
-        raise TypeError(f"the device sun-zenith correction works on float32 data, got {data.dtype}")
+    if data.dtype not in ((torch.float32, torch.float64) if allow_f64 else (torch.float32,)):
+        raise TypeError(f"the device sun-zenith correction works on float32/float64 data, got {data.dtype}")
     return (data if data.is_cuda else data.to("cuda")).contiguous(), False
 
 
@@ -86,7 +87,8 @@ def sunz_correct(data, area=None, start_time=None, correction_limit=88.0, max_sz
     that ``data`` covers (row-tiled multi-GPU use).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
     """
     torch = _lib.require_cuda()
-    t, was_numpy = _to_cuda_f32(torch, data)
+    t, was_numpy = _to_cuda_f32(torch, data, allow_f64=True)
+    f64 = t.dtype == torch.float64
     if t.dim() not in (2, 3):
         raise ValueError("data must be (y, x) or (bands, y, x)")
     nbands = 1 if t.dim() == 2 else t.shape[0]
@@ -102,16 +104,18 @@ def sunz_correct(data, area=None, start_time=None, correction_limit=88.0, max_sz
         if w != area.width or row0 + h > area.height:
             raise IncompatibleAreas(f"data shape {(h, w)} (row offset {row0}) does not fit area shape {area.shape}")
         g = area.geo_struct(row0, h)
-        s = _sunz_struct(start_time, correction_limit, max_sza, True, meth)
-        _lib.check(lib.b200_sunz_correct(t.data_ptr(), out.data_ptr(), nbands, h * w, C.byref(g), C.byref(s),
-                                         _lib.stream_ptr(torch)))
+        s = _sunz_struct(start_time, correction_limit, max_sza, not f64, meth)
+        fn = lib.b200_sunz_correct_f64 if f64 else lib.b200_sunz_correct
+        _lib.check(fn(t.data_ptr(), out.data_ptr(), nbands, h * w, C.byref(g), C.byref(s), _lib.stream_ptr(torch)))
     else:
-        z, _ = _to_cuda_f32(torch, sza)
+        z, _ = _to_cuda_f32(torch, sza, allow_f64=True)
         if tuple(z.shape) != (h, w):
             raise IncompatibleAreas(f"sza shape {tuple(z.shape)} != data shape {(h, w)}")
-        s = _sunz_struct(None, correction_limit, max_sza, True, meth)
-        _lib.check(lib.b200_sunz_correct_sza(t.data_ptr(), z.data_ptr(), out.data_ptr(), nbands, h * w, h * w,
-                                             C.byref(s), _lib.stream_ptr(torch)))
+        z = z.to(t.dtype)
+        s = _sunz_struct(None, correction_limit, max_sza, not f64, meth)
+        fn = lib.b200_sunz_correct_sza_f64 if f64 else lib.b200_sunz_correct_sza
+        _lib.check(fn(t.data_ptr(), z.data_ptr(), out.data_ptr(), nbands, h * w, h * w, C.byref(s),
+                      _lib.stream_ptr(torch)))
     return out.cpu().numpy() if was_numpy else out
 
 

@@ -174,6 +174,35 @@ def test_sunz_corrector_golden_not_provided():
     np.testing.assert_allclose(res.values, np.array([[66.853262, 68.168939], [66.30742, 67.601493]]), rtol=1e-5)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sunz_corrector_golden_both_dtypes(dtype):
+    """The reference runs these cases for float32 AND float64 data (satpy/tests/test_modifiers.py:116-176)."""
+    area = _sunz_area()
+    attrs = {"area": area, "start_time": dt.datetime(2018, 1, 1, 18), "modifiers": tuple(), "name": "test_vis"}
+    ds = DataArrayLite(np.ones((2, 2), dtype=dtype), ("y", "x"), attrs)
+    sza = DataArrayLite(np.rad2deg(np.arccos(np.array([[0.0149581333, 0.0146694376], [0.0150812684, 0.0147925727]])))
+                        .astype(dtype), ("y", "x"), {"area": area})
+    for args in ((ds,), (ds, sza)):
+        res = SunZenithCorrector(name="sza_test", modifiers=tuple())(args, test_attr="test")
+        assert res.dtype == dtype and res.values.dtype == dtype
+        np.testing.assert_allclose(res.values, np.array([[22.401667, 22.31777], [22.437503, 22.353533]], dtype=dtype),
+                                   rtol=2e-6)
+        res = SunZenithCorrector(name="sza_test", modifiers=tuple(), correction_limit=90)(args, test_attr="test")
+        np.testing.assert_allclose(res.values, np.array([[66.853262, 68.168939], [66.30742, 67.601493]], dtype=dtype),
+                                   rtol=1e-5)
+
+
+def test_sunz_correct_float64_matches_oracle():
+    area, oarea = both_areas("goes_east_abi_f_2km", 500 / 5424)
+    when = dt.datetime(2019, 3, 14, 23, 30)
+    data = np.random.default_rng(5).uniform(0, 120, size=area.shape)
+    res = sunz_correct(data, area=area, start_time=when)
+    ref = osolar.sun_zenith_corrector(data, oarea, when)
+    assert res.dtype == np.float64
+    np.testing.assert_array_equal(np.isnan(res), np.isnan(ref))
+    np.testing.assert_allclose(res, ref, rtol=1e-9, atol=1e-9)   # float64 throughout: no float32 trig in the way
+
+
 def test_sunz_corrector_golden_provided():
     """satpy/tests/test_modifiers.py:148-176: SZA given as an optional dataset."""
     area = _sunz_area()
