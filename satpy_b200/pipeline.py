@@ -63,7 +63,7 @@ class ABIResamplePipeline:
         cptr = (C.c_void_p * 1)(counts_dev.data_ptr())
         optr = (C.c_void_p * 1)(self.refl.data_ptr())
         _lib.check(self.lib.b200_abi_vis_sunz(cptr, optr, s_cal, 1, C.byref(g), C.byref(sz), _lib.stream_ptr(torch)))
-        self.launches += 1
+        self.launches += 2  # geos_tables_kernel + abi_vis_sunz_kernel
         return self.refl
 
     def build_grid(self):
@@ -78,7 +78,7 @@ class ABIResamplePipeline:
                                                    _lib.stream_ptr(torch)))
         self.grid = _Grid(handle)
         self.n_valid = int(n_valid.value)
-        self.launches += 2
+        self.launches += 2  # geos_tables_kernel + nn_source_points_kernel (the cub scan kernels are not counted)
         return self.grid
 
     def query_gather(self, data, out, fill=float("nan"), row_window=None):
@@ -90,7 +90,7 @@ class ABIResamplePipeline:
         _lib.check(self.lib.b200_nn_query_gather_f32(self.grid.handle, C.byref(gd), self.radius, data.data_ptr(),
                                                      out.data_ptr(), 1, self.refl.numel(), out.numel(), fill,
                                                      _lib.stream_ptr(torch)))
-        self.launches += 1
+        self.launches += 3  # nn_target_tables_kernel + nn_seg_cmax_kernel + nn_fixed_query_rect_kernel
         return out
 
     def query(self):

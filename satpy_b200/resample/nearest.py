@@ -20,7 +20,10 @@ same two geometries (the analogue of ``self._index_caches``, kdtree.py:58,140).
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
+import json
 import logging
+import os
 
 import numpy as np
 
@@ -108,17 +111,22 @@ class B200NearestResampler:
 
         ``row_window=(row0, nrows)`` restricts the search to a band of target rows (row-tiled
         multi-GPU use); the default is the whole target.  ``epsilon`` is accepted for signature
-        compatibility: the search is always exact (epsilon = 0).  ``cache_dir`` is not used: the
-        neighbour info is cached in device memory on this instance.  ``method``: ``"auto"`` (fixed-grid
+        compatibility: the search is always exact (epsilon = 0).  The neighbour info is cached in device
+        memory on this instance; with ``cache_dir`` it is also written to / read from ``nn_lut-<hash>.npz``
+        (the reference's zarr cache, kdtree.py:125-177, with the same array names).  ``method``: ``"auto"`` (fixed-grid
         search for geostationary area sources, bucket grid otherwise), ``"bucket"`` or ``"fixed_grid"``;
         both engines return identical indices.
         """
-        del kwargs, cache_dir
+        del kwargs
         torch = _lib.require_cuda()
         lib = _lib.load()
         if radius_of_influence is None:
             radius_of_influence = self._default_radius()
         radius = float(radius_of_influence)
+        if mask is not None and cache_dir:
+            LOG.warning("Mask and cache_dir both provided to nearest resampler. Cached parameters are affected by "
+                        "masked pixels. Will not cache results.")   # kdtree.py:69-73
+            cache_dir = None
         src, dst = self.source_geo_def, self.target_geo_def
         row0, nrows = (0, dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
         key = (radius, row0, nrows, method)
@@ -126,6 +134,14 @@ class B200NearestResampler:
             self._current = self._index_caches[key]
             LOG.debug("Reusing device-resident neighbour info")
             return key
+        if cache_dir and row_window is None:
+            try:
+                self.load_cached_neighbour_info(cache_dir, radius, epsilon)
+                LOG.debug("Read pre-computed kd-tree parameters")
+                self._index_caches[key] = self._current
+                return key
+            except IOError:
+                LOG.debug("Computing kd-tree parameters")
         LOG.debug("Computing bucket-grid neighbour info")
         mask_ptr = None
         if mask is not None:
@@ -158,7 +174,49 @@ class B200NearestResampler:
         if mask is None:
             self._index_caches[key] = info
         self._current = info
+        if cache_dir and row_window is None:
+            self.save_neighbour_info(cache_dir, radius, epsilon)
         return key
+
+    # --------------------------------------------------------------- cache on disk
+    def _cache_filename(self, cache_dir, radius, epsilon=0):
+        """``nn_lut-<hash>.npz``: the reference hashes the two geometries and the search keywords into
+        ``nn_lut-<hash>.zarr`` (satpy/resample/kdtree.py:116-123); zarr is not available here, the array names and
+        dims are the reference's (``NN_COORDINATES``)."""
+        def describe(geo):
+            if isinstance(geo, AreaDefinition):
+                return {"proj": {k: str(v) for k, v in sorted(geo.proj_dict.items())}, "shape": geo.shape,
+                        "extent": geo.area_extent}
+            lo = payload_to_numpy(geo.lons)
+            la = payload_to_numpy(geo.lats)
+            return {"swath": hashlib.sha1(np.ascontiguousarray(lo).tobytes() + np.ascontiguousarray(la).tobytes()).hexdigest()}
+        key = json.dumps({"src": describe(self.source_geo_def), "dst": describe(self.target_geo_def),
+                          "radius_of_influence": radius, "epsilon": epsilon, "neighbours": 1}, sort_keys=True)
+        return os.path.join(cache_dir, "nn_lut-" + hashlib.sha1(key.encode()).hexdigest() + ".npz")
+
+    def save_neighbour_info(self, cache_dir, radius_of_influence, epsilon=0):
+        """Persist the three index arrays (``save_neighbour_info``, satpy/resample/kdtree.py:158-177)."""
+        if not cache_dir:
+            return None
+        os.makedirs(cache_dir, exist_ok=True)
+        filename = self._cache_filename(cache_dir, float(radius_of_influence), epsilon)
+        info = self.neighbour_info()
+        np.savez_compressed(filename, **info)
+        LOG.info("Saving kd_tree neighbour info to %s", filename)
+        return filename
+
+    def load_cached_neighbour_info(self, cache_dir, radius_of_influence, epsilon=0):
+        """Re-install index arrays saved earlier (``load_neighbour_info``, kdtree.py:125-156); ``IOError`` when the
+        cache has no entry for these geometries and keywords, like the reference."""
+        if not cache_dir:
+            raise IOError
+        filename = self._cache_filename(cache_dir, float(radius_of_influence), epsilon)
+        if not os.path.exists(filename):
+            raise IOError(f"no cached neighbour info {filename}")
+        with np.load(filename) as fid:
+            self.load_neighbour_info(fid["valid_input_index"], fid["index_array"], fid["valid_output_index"])
+        self._index_caches[(float(radius_of_influence), 0, self.target_geo_def.height, "auto")] = self._current
+        return filename
 
     def neighbour_info(self, as_numpy=True):
         """The reference's three cached arrays (names/dims as ``NN_COORDINATES``)."""

@@ -678,3 +678,28 @@ def test_gather_into_misaligned_row_band():
         view.fill_(-7.0)
         pipe.gather(pipe.refl, view)
         np.testing.assert_array_equal(view.cpu().numpy(), ref[row0:row0 + nrows])
+
+
+def test_nearest_cache_dir_round_trip(tmp_path):
+    """cache_dir persistence (satpy/resample/kdtree.py:125-177): a second resampler loads the index arrays from disk
+    (no search) and gives the same image; a mask disables caching like in the reference."""
+    src, _ = both_areas("goes_east_abi_f_2km", 300 / 5424)
+    dst, _ = both_areas("goes_east_eqc_2km", 400 / 9050)
+    data = np.random.default_rng(2).uniform(0, 1, size=src.shape).astype(np.float32)
+    r1 = B200NearestResampler(src, dst)
+    out1 = r1.resample(data, radius_of_influence=60e3, cache_dir=str(tmp_path))
+    files = list(tmp_path.glob("nn_lut-*.npz"))
+    assert len(files) == 1
+    with np.load(files[0]) as fid:
+        assert set(fid.files) == {"valid_input_index", "valid_output_index", "index_array"}
+        assert fid["index_array"].shape == dst.shape + (1,)
+    r2 = B200NearestResampler(src, dst)
+    r2.load_cached_neighbour_info(str(tmp_path), 60e3)
+    np.testing.assert_array_equal(r2.compute(data), out1)
+    r3 = B200NearestResampler(src, dst)
+    np.testing.assert_array_equal(r3.resample(data, radius_of_influence=60e3, cache_dir=str(tmp_path)), out1)
+    with pytest.raises(IOError):
+        B200NearestResampler(src, dst).load_cached_neighbour_info(str(tmp_path), 61e3)
+    B200NearestResampler(src, dst).resample(data, radius_of_influence=61e3, cache_dir=str(tmp_path),
+                                            mask=np.zeros(src.shape, bool))
+    assert len(list(tmp_path.glob("nn_lut-*.npz"))) == 1
