@@ -703,3 +703,28 @@ def test_nearest_cache_dir_round_trip(tmp_path):
     B200NearestResampler(src, dst).resample(data, radius_of_influence=61e3, cache_dir=str(tmp_path),
                                             mask=np.zeros(src.shape, bool))
     assert len(list(tmp_path.glob("nn_lut-*.npz"))) == 1
+
+
+def test_row_blocks_with_source_windows_reassemble_the_full_image():
+    """The multi-GPU decomposition on one GPU: every target row block, fed only the band of source rows that can reach
+    it (satpy_b200.parallel.source_row_window, the analogue of get_area_slices), reproduces its rows of the full run."""
+    import torch
+    from satpy_b200 import parallel
+    from satpy_b200.pipeline import ABIResamplePipeline
+    s, d = 900 / 10848, 1802 / 80150
+    src, dst = demo.make_area("goes_east_abi_f_1km", s), demo.make_area("global_eqc_500m", d)
+    counts = demo.abi_counts(src.shape, seed=7, band="C02")
+    cdev = torch.from_numpy(counts).cuda()
+    cal = demo.abi_calibration("C02")
+    radius = 2.2 * 1002.0 / s
+    full = ABIResamplePipeline(src, dst, radius).run(cdev, cal, demo.START_TIME).cpu().numpy()
+    block_rows, blocks = parallel.row_tiles(dst.height, 8)
+    assert sum(n for _, n in blocks) == dst.height
+    n_src_rows = 0
+    for row0, nrows in blocks:
+        s0, sn = parallel.source_row_window(src, dst, row0, nrows, radius)
+        n_src_rows += sn
+        pipe = ABIResamplePipeline(src, dst, radius, row_window=(row0, nrows), src_row_window=(s0, sn))
+        out = pipe.run(cdev[s0:s0 + sn].contiguous(), cal, demo.START_TIME).cpu().numpy()
+        np.testing.assert_array_equal(out, full[row0:row0 + nrows])
+    assert n_src_rows < 1.6 * src.height          # the windows overlap a little, they do not replicate the source
