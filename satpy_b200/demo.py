@@ -27,6 +27,12 @@ AREAS = {
     # satpy/etc/areas.yaml:531-548
     "goes_east_abi_f_1km": ({"proj": "geos", "sweep": "x", "lon_0": -75.0, "h": 35786023.0, "ellps": "GRS80"},
                             10848, 10848, (-5434894.885056, -5434894.885056, 5434894.885056, 5434894.885056)),
+    # satpy/etc/areas.yaml:287-302 (config 3 source); lon_0 = 140.7: the visible disk crosses the antimeridian
+    "himawari_ahi_fes_1km": ({"proj": "geos", "lon_0": 140.7, "a": 6378137.0, "rf": 298.257024882273, "h": 35785863.0},
+                             11000, 11000, (-5500000.0355, -5500000.0355, 5500000.0355, 5500000.0355)),
+    # 1 km Lambert conformal conic over East Asia (config 3 target, builder-fixed: SURVEY.md section 8d)
+    "east_asia_lcc_1km": ({"proj": "lcc", "lat_1": 30.0, "lat_2": 60.0, "lat_0": 38.0, "lon_0": 126.0, "ellps": "WGS84"},
+                          6000, 6000, (-3.0e6, -3.0e6, 3.0e6, 3.0e6)),
     # "1 km EuroLAEA" (config 1): ETRS89-LAEA (EPSG:3035) parameters, 5000 x 4500 pixels of 1 km
     "euro_laea_1km": ({"proj": "laea", "lat_0": 52.0, "lon_0": 10.0, "x_0": 4321000.0, "y_0": 3210000.0,
                        "ellps": "GRS80"}, 5000, 4500, (2500000.0, 1400000.0, 7500000.0, 5900000.0)),

@@ -124,16 +124,16 @@ def main():
     rec("nn_gather_kernel<u32> x3 bands", "C2 gather 3 x 81.9 Mpix", ms, (4 + 3 * 4) * d2.size + 3 * 4 * r2._current["n_valid"])
     del r2, rgb
 
-    # ---- config 3 (reduced source: AHI 1 km 11000^2 needs the himawari area; use ABI 1 km as the same geometry class)
-    d3 = AreaDefinition("lcc", "lcc", "lcc", {"proj": "lcc", "lat_1": 25.0, "lat_2": 45.0, "lat_0": 35.0, "lon_0": -95.0,
-                                              "ellps": "WGS84"}, 6000, 6000, (-3.0e6, -3.0e6, 3.0e6, 3.0e6))
-    rb = B200BilinearResampler(src, d3)
+    # ---- config 3: AHI 11000^2 (1 km) -> 1 km LCC 6000^2, bilinear, 32 neighbours, radius 50 km
+    s3, d3 = demo.make_area("himawari_ahi_fes_1km"), demo.make_area("east_asia_lcc_1km")
+    rb = B200BilinearResampler(s3, d3)
     ms = timeit(lambda: (setattr(rb, "_info", None), rb.precompute(radius_of_influence=50000.0)), steps=2, warmup=1)
-    rec("b200_bil_info", "C3-like: 10848^2 geos 1 km -> 6000^2 LCC 1 km, 32 neighbours, r=50 km", ms, 32 * d3.size,
-        "k-nearest + quadrant corners + (s, t); latency / float64 bound")
-    ms = timeit(lambda: rb.compute(data))
-    rec("bil_sample_f32_kernel", "C3-like sample 36 Mpix", ms, 36 * d3.size)
-    del rb
+    rec("nn_grid_create + b200_bil_info", "C3 bilinear info: AHI 11000^2 -> 6000^2 LCC, 32 neighbours, r=50 km", ms,
+        32 * d3.size, "k-nearest + quadrant corners + (s, t); float64 projection / latency bound")
+    ahi = torch.rand(s3.shape, device="cuda") * 300
+    ms = timeit(lambda: rb.compute(ahi))
+    rec("bil_sample_f32_kernel", "C3 sample 36 Mpix", ms, 36 * d3.size)
+    del rb, ahi
 
     # ---- config 4: VIIRS M-band-like swath 7680 x 3200, EWA to a 750 m polar stereographic grid
     lon, lat, rps = demo.viirs_like_swath(nscans=480, rows_per_scan=16, ncols=3200)

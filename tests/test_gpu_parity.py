@@ -728,3 +728,27 @@ def test_row_blocks_with_source_windows_reassemble_the_full_image():
         out = pipe.run(cdev[s0:s0 + sn].contiguous(), cal, demo.START_TIME).cpu().numpy()
         np.testing.assert_array_equal(out, full[row0:row0 + nrows])
     assert n_src_rows < 1.6 * src.height          # the windows overlap a little, they do not replicate the source
+
+
+def test_config3_geometry_bilinear_and_nearest_across_the_antimeridian():
+    """Config 3 geometry in miniature: Himawari (lon_0 = 140.7, disk crossing +-180) -> LCC over East Asia; also a
+    global grid so that both sides of the antimeridian are hit."""
+    from oracle import bilinear as obil
+    from satpy_b200.resample import B200BilinearResampler
+    src, o_src = both_areas("himawari_ahi_fes_1km", 700 / 11000)
+    dst, o_dst = both_areas("east_asia_lcc_1km", 300 / 6000)
+    r = B200BilinearResampler(src, dst)
+    r.precompute(radius_of_influence=50e3 * 11000 / 700 / 4)
+    info = r.bil_info()
+    t, s, vin, idx = obil.get_bil_info(o_src, o_dst, 50e3 * 11000 / 700 / 4, 32)
+    both = np.isfinite(t) & np.isfinite(s) & np.isfinite(info["bilinear_t"]) & np.isfinite(info["bilinear_s"])
+    assert both.mean() > 0.9
+    same = (info["index_array"][both] == idx[both]).all(axis=1)
+    assert same.mean() > 0.9999
+    glob, o_glob = both_areas("global_eqc_500m", 1200 / 80150)
+    rn = B200NearestResampler(src, glob)
+    rn.precompute(radius_of_influence=30e3)
+    vin, ref, got, n_tie = _check_indices(rn, o_src, o_glob, 30e3)
+    lon, _ = o_glob.get_lonlats()
+    hit = got >= 0
+    assert (hit & (lon > 170)).any() and (hit & (lon < -170)).any()   # neighbours found on both sides of +-180
