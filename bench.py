@@ -51,8 +51,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--subtiles", type=int, default=0,
                     help="N > 1: row blocks per rank, each group of N blocks all-gathered while the next is searched; "
-                         "0 = automatic (4 at N = 2 where the search dominates, 1 = one all-gather at N >= 4 where the "
-                         "exchange dominates: measured 21.6 ms vs 31.5 ms per step at N = 8)")
+                         "0 = automatic: max(1, 8 // N), the measured optimum at N = 2, 4 and 8")
     return ap.parse_args()
 
 
@@ -188,7 +187,9 @@ def run_reference(args):
 def effective_subtiles(args):
     if args.gpus <= 1:
         return 1
-    return args.subtiles if args.subtiles > 0 else (4 if args.gpus == 2 else 1)
+    # automatic: keep every rank's contribution to one all-gather near total / 8 (1.6 GB for config 5).  Measured on
+    # 8 x B200 (ms per step): N=2 S=1 31.0, S=4 22.5 | N=4 S=1 33.2, S=2 20.5, S=4 30.4 | N=8 S=1 21.6, S=2 31.5, S=4 30.5
+    return args.subtiles if args.subtiles > 0 else max(1, 8 // args.gpus)
 
 
 def config_dict(sp, dp, radius, args):
