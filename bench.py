@@ -251,7 +251,7 @@ def run_b200(args):
                        "out": full[b * block_rows: b * block_rows + nrows],
                        "slot": full[b * block_rows: (b + 1) * block_rows],
                        "group": full[k * world * block_rows: (k + 1) * world * block_rows]})
-    comm_stream = torch.cuda.Stream() if world > 1 else None
+    comm_stream = torch.cuda.Stream(priority=-1) if world > 1 else None   # the exchange gets SMs first
 
     def step():
         main = torch.cuda.current_stream()

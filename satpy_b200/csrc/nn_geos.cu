@@ -333,6 +333,7 @@ nn_seg_cmax_kernel(const TgtCol *__restrict__ cols, int W, int nseg, float *__re
 // handed out in order through an atomic counter (chunks of GEOS_CHUNK consecutive segments).
 // FUSED1: the hot configuration -- fused gather of one float32 band, no index outputs.
 #define GEOS_CHUNK 16
+#define GEOS_CHUNKS_PER_CTA 8
 template <bool FUSED1>
 __global__ void __launch_bounds__(256, 4)
 nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long long *__restrict__ queue,
@@ -342,7 +343,10 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
     const long long items = (long long)Q.dst.nrows * nseg;
     const int lane = threadIdx.x & 31;
     __shared__ int s_row, s_seg, s_count;
-    for (;;) {
+    // Each CTA takes GEOS_CHUNKS_PER_CTA chunks from the queue and retires: CTAs keep sweeping one compact front of
+    // target rows (the queue hands chunks out in order), but SM slots free up all the time, so that a collective
+    // issued on another stream (the all-gather of the previous row block) gets SMs while this kernel runs.
+    for (int turn = 0; turn < GEOS_CHUNKS_PER_CTA; ++turn) {
         if (threadIdx.x == 0) {
             long long first = (long long)atomicAdd(queue, (unsigned long long)GEOS_CHUNK);
             long long left = items - first;
@@ -481,7 +485,9 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
         if (e == cudaSuccess) {
             nn_seg_cmax_kernel<<<(nseg * 32 + 255) / 256, 256, 0, s>>>(cols, (int)dst->width, nseg, seg_cmax);
             int64_t items = dst->nrows * (int64_t)nseg;
-            int grid = b200_grid_for((items + GEOS_CHUNK - 1) / GEOS_CHUNK, 1, 4);
+            const int64_t chunks = (items + GEOS_CHUNK - 1) / GEOS_CHUNK;
+            int grid = (int)((chunks + GEOS_CHUNKS_PER_CTA - 1) / GEOS_CHUNKS_PER_CTA);
+            if (grid < 1) grid = 1;
             const bool fused1 = O.out != nullptr && O.nbands == 1 && !O.index_array && !O.gather_index &&
                                 !O.valid_output;
             if (fused1)
