@@ -752,3 +752,41 @@ def test_config3_geometry_bilinear_and_nearest_across_the_antimeridian():
     lon, _ = o_glob.get_lonlats()
     hit = got >= 0
     assert (hit & (lon > 170)).any() and (hit & (lon < -170)).any()   # neighbours found on both sides of +-180
+
+
+def test_c_abi_edge_cases_and_errors():
+    """Empty and degenerate inputs and the documented error codes, straight through the C ABI."""
+    import ctypes as C
+    import torch
+    from satpy_b200 import _lib
+    lib = _lib.load()
+    stream = _lib.stream_ptr(torch)
+    # n = 0 is a no-op everywhere, NULL pointers allowed then
+    cal = demo.abi_calibration("C02").struct("radiance")
+    assert lib.b200_abi_calibrate(None, None, 0, C.byref(cal), stream) == 0
+    fill = (C.c_char * 4)()
+    assert lib.b200_nn_gather(None, None, None, 0, 1, 0, 0, 4, C.cast(fill, C.c_void_p), stream) == 0
+    # bad arguments -> B200_EINVAL with a message, never a crash
+    assert lib.b200_abi_calibrate(None, None, 8, C.byref(cal), stream) == _lib.B200_EINVAL
+    assert b"NULL" in lib.b200_last_error()
+    assert lib.b200_nn_gather(None, None, None, 4, 1, 0, 0, 3, C.cast(fill, C.c_void_p), stream) == _lib.B200_EINVAL
+    # a 1 x 1 target and a 2 x 2 source
+    src = AreaDefinition("s", "s", "s", {"proj": "geos", "lon_0": 0.0, "h": 35785831.0, "ellps": "WGS84"}, 2, 2,
+                         (-3000.0, -3000.0, 3000.0, 3000.0))
+    dst = AreaDefinition("d", "d", "d", {"proj": "eqc", "lon_0": 0.0, "ellps": "WGS84"}, 1, 1, (-1500.0, -1500.0, 1500.0, 1500.0))
+    for method in ("bucket", "fixed_grid"):
+        r = B200NearestResampler(src, dst)
+        out = r.resample(np.array([[1, 2], [3, 4]], np.float32), radius_of_influence=5000.0, method=method)
+        assert out.shape == (1, 1) and out[0, 0] in (1, 2, 3, 4)   # four equidistant pixels: lowest index wins
+        assert out[0, 0] == 1
+    # a radius of more than 4096 source pixels is refused by the fixed-grid engine, served by the bucket engine
+    big = B200NearestResampler(src, dst)
+    with pytest.raises(NotImplementedError, match="bucket"):
+        big.precompute(radius_of_influence=2.0e7, method="fixed_grid")
+    big.precompute(radius_of_influence=2.0e7, method="bucket")
+    assert big.neighbour_info()["index_array"][0, 0, 0] == 0
+    # a swath whose every pixel is invalid: nothing to find, no crash
+    nan_swath = SwathDefinition(np.full((4, 5), np.nan), np.full((4, 5), np.nan))
+    rs = B200NearestResampler(nan_swath, dst)
+    res = rs.resample(np.ones((4, 5), np.float32), radius_of_influence=1e5)
+    assert np.isnan(res).all() and rs._current["n_valid"] == 0
