@@ -181,6 +181,16 @@ int b200_sunz_correct_f64(const double *data, double *out, int32_t nbands, int64
 int b200_sunz_correct_sza_f64(const double *data, const double *sza_deg, double *out, int32_t nbands,
                               int64_t band_stride, int64_t n, const b200_sunz_t *sz, void *stream);
 
+/* get_angles (modifiers/angles.py:377-402,443-531 + pyorbital get_observer_look / get_alt_az): sensor azimuth
+ * and zenith, solar azimuth (0..360) and zenith, degrees, float64, NaN where the area has no lon/lat.  Any output
+ * may be NULL.  sz supplies gmst / ra / dec of start_time; the satellite position is the one get_satpos returns
+ * (longitude, latitude in degrees, altitude in km). */
+int b200_get_angles(const b200_geo_t *geo, const b200_sunz_t *sz, double sat_lon, double sat_lat, double sat_alt_km,
+                    double *sata, double *satz, double *suna, double *sunz, void *stream);
+/* compute_relative_azimuth (modifiers/angles.py:336-374): min(|sun - sat|, 360 - |sun - sat|). */
+int b200_relative_azimuth(const void *sat_azi, const void *sun_azi, void *out, int64_t n, int32_t is_f32,
+                          void *stream);
+
 /* SunZenithReducer (modifiers/geometry.py:166-207 -> angles.py:594-624): out = data * reduction(sza). */
 int b200_sunz_reduce(const float *data, const float *sunz_deg, float *out, int32_t nbands, int64_t band_stride,
                      int64_t n, float limit_deg, float max_sza_deg, float strength, void *stream);

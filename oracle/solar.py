@@ -160,3 +160,71 @@ def as_datetime(t) -> dt.datetime:
     if isinstance(t, dt.datetime):
         return t
     return np.datetime64(t, "us").astype(dt.datetime)
+
+
+# =====================================================================================================================
+# Sensor / sun angles ("next" row of SURVEY.md section 8f): satpy/modifiers/angles.py:336-402,443-531.
+# pyorbital (un-vendored, unpinned) supplies get_observer_look / observer_position / get_alt_az; restated from the
+# library's published code (Celestrak "Orbital Coordinate Systems" parts II and III).  UNPINNED except
+# compute_relative_azimuth (satpy/tests/modifier_tests/test_angles.py:361-382).
+_F = 1 / 298.257223563   # WGS-84 flattening (pyorbital.astronomy.F)
+_A = 6378.137            # WGS-84 equatorial radius [km] (pyorbital.astronomy.A)
+
+
+def observer_position(utc_time, lon, lat, alt):
+    """ECI position [km] of a point at geodetic lon/lat [deg] and altitude [km] (pyorbital ``observer_position``)."""
+    lon = np.deg2rad(lon)
+    lat = np.deg2rad(lat)
+    theta = (gmst(utc_time) + lon) % (2 * np.pi)
+    c = 1 / np.sqrt(1 + _F * (_F - 2) * np.sin(lat) ** 2)
+    sq = c * (1 - _F) ** 2
+    achcp = (_A * c + alt) * np.cos(lat)
+    return achcp * np.cos(theta), achcp * np.sin(theta), (_A * sq + alt) * np.sin(lat)
+
+
+def get_observer_look(sat_lon, sat_lat, sat_alt, utc_time, lon, lat, alt):
+    """(azimuth, elevation) [deg] of the satellite seen from the ground (pyorbital ``orbital.get_observer_look``)."""
+    pos_x, pos_y, pos_z = observer_position(utc_time, sat_lon, sat_lat, sat_alt)
+    opos_x, opos_y, opos_z = observer_position(utc_time, lon, lat, alt)
+    lon = np.deg2rad(lon)
+    lat = np.deg2rad(lat)
+    theta = (gmst(utc_time) + lon) % (2 * np.pi)
+    rx, ry, rz = pos_x - opos_x, pos_y - opos_y, pos_z - opos_z
+    sin_lat, cos_lat, sin_theta, cos_theta = np.sin(lat), np.cos(lat), np.sin(theta), np.cos(theta)
+    top_s = sin_lat * cos_theta * rx + sin_lat * sin_theta * ry - cos_lat * rz
+    top_e = -sin_theta * rx + cos_theta * ry
+    top_z = cos_lat * cos_theta * rx + cos_lat * sin_theta * ry + sin_lat * rz
+    az_ = np.mod(np.arctan2(-top_e, top_s) + np.pi, 2 * np.pi)
+    rg_ = np.sqrt(rx * rx + ry * ry + rz * rz)
+    with np.errstate(invalid="ignore"):
+        el_ = np.arcsin((top_z / rg_).clip(max=1))
+    return np.rad2deg(az_), np.rad2deg(el_)
+
+
+def get_alt_az(utc_time, lon, lat):
+    """Sun altitude and azimuth [rad] (pyorbital ``astronomy.get_alt_az``)."""
+    lon = np.deg2rad(lon)
+    lat = np.deg2rad(lat)
+    ra_, dec = sun_ra_dec(utc_time)
+    h__ = (gmst(utc_time) + lon) - ra_
+    alt_ = np.arcsin(np.sin(lat) * np.sin(dec) + np.cos(lat) * np.cos(dec) * np.cos(h__))
+    az_ = np.arctan2(-np.sin(h__), (np.cos(lat) * np.tan(dec) - np.sin(lat) * np.cos(h__)))
+    return alt_, az_
+
+
+def get_angles(area, start_time, sat_lon, sat_lat, sat_alt_m):
+    """``get_angles`` (satpy/modifiers/angles.py:377-402): sensor azimuth / zenith, solar azimuth / zenith [deg], float64."""
+    lons, lats = area.get_lonlats()
+    with np.errstate(invalid="ignore"):
+        lons = np.where(lons >= 1e30, np.nan, lons)
+        lats = np.where(lats >= 1e30, np.nan, lats)
+        sata, satel = get_observer_look(sat_lon, sat_lat, sat_alt_m / 1000.0, start_time, lons, lats, 0)
+        suna = np.rad2deg(get_alt_az(start_time, lons, lats)[1]) % 360.
+        sunz = np.rad2deg(np.arccos(cos_zen(start_time, lons, lats)))
+    return sata, 90 - satel, suna, sunz
+
+
+def compute_relative_azimuth(sat_azi, sun_azi):
+    """satpy/modifiers/angles.py:371-374."""
+    ssadiff = np.absolute(sun_azi - sat_azi)
+    return np.minimum(ssadiff, sun_azi.dtype.type(360.0) - ssadiff)

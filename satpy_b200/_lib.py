@@ -89,6 +89,8 @@ SIGNATURES = {
     "b200_seviri_calibrate": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(SeviriCalStruct), _P]),
     "b200_viirs_scale": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                    C.c_int32, C.c_int32, C.c_float, _P]),
+    "b200_get_angles": (C.c_int, [_GEO, C.POINTER(SunzStruct), C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P]),
+    "b200_relative_azimuth": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
     "b200_sunz_reduce": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, _P]),
     "b200_cos_sza": (C.c_int, [_GEO, C.POINTER(SunzStruct), _P, _P]),
     "b200_sunz_correct": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _GEO, C.POINTER(SunzStruct), _P]),

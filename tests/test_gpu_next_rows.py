@@ -210,3 +210,38 @@ def test_config2_chain_matches_oracle():
     ok = ~np.isnan(green) & ~np.isnan(ref_green)
     err = np.abs(green[ok] - ref_green[ok]) / np.maximum(np.abs(ref_green[ok]), 1e-3)
     assert ok.mean() > 0.3 and (err > 1e-5).mean() < 2e-3   # equidistant ties may pick the twin pixel
+
+
+def test_get_angles_matches_oracle_and_relative_azimuth_golden():
+    """satpy/modifiers/angles.py:336-402 on the device; relative azimuth golden: test_angles.py:361-382."""
+    from oracle.projections import Area as OArea
+    from satpy_b200 import demo
+    from satpy_b200.modifiers.angles import compute_relative_azimuth, get_angles, get_satellite_zenith_angle
+    scale = 400 / 5424
+    area, oarea = demo.make_area("goes_east_abi_f_2km", scale), OArea(*demo.area_params("goes_east_abi_f_2km", scale))
+    when = dt.datetime(2019, 3, 14, 18, 0)
+    ds = DataArrayLite(np.zeros(area.shape, np.float32), ("y", "x"),
+                       {"area": area, "start_time": when,
+                        "orbital_parameters": {"satellite_nominal_longitude": -75.2, "satellite_nominal_latitude": 0.03,
+                                               "satellite_nominal_altitude": 35786023.0}})
+    sata, satz, suna, sunz = get_angles(ds)
+    ref = osolar.get_angles(oarea, when, -75.2, 0.03, 35786023.0)
+    for got, exp, name in zip((sata, satz, suna, sunz), ref, ("sata", "satz", "suna", "sunz")):
+        assert got.dtype == np.float64
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+        ok = ~np.isnan(exp)
+        d = np.abs(got[ok] - exp[ok])
+        if name in ("sata", "suna"):
+            d = np.minimum(d, 360.0 - d)   # azimuth wraps; near the sub-satellite / sub-solar point it is ill-conditioned
+            assert np.quantile(d, 0.999) < 1e-6, name
+        else:
+            assert d.max() < 1e-7, name
+    assert np.nanmin(satz) < 1.0 and 85 < np.nanmax(satz) < 92
+    np.testing.assert_array_equal(get_satellite_zenith_angle(ds), satz)
+    for dtype in (np.float32, np.float64):
+        saa = np.array([-120, 40., 0.04, 179.4, 94.2, 12.1], dtype=dtype)
+        vaa = np.array([60., 57.7, 175.1, 234.18, 355.4, 12.1], dtype=dtype)
+        raa = compute_relative_azimuth(vaa, saa)
+        assert raa.dtype == dtype
+        np.testing.assert_allclose(np.array([180., 17.7, 175.06, 54.78, 98.8, 0.], dtype=dtype), raa, rtol=2e-7)
+        np.testing.assert_array_equal(raa, osolar.compute_relative_azimuth(vaa, saa))

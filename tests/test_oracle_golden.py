@@ -272,3 +272,26 @@ def test_viirs_scale():
     np.testing.assert_array_equal(out, np.array([[1, 201], [131055, np.nan], [99, np.nan], [1.5, 2.0]], np.float32))
     out = ocal.viirs_scale(np.array([[1.0, -999.0], [-999.5, 3.0]], np.float32), [-999.9, 0.0, 1.0, 1.0], [1, 1])
     assert np.isnan(out[0]).all() and np.isnan(out[1, 0]) and out[1, 1] == 4.0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_relative_azimuth_golden(dtype):
+    """satpy/tests/modifier_tests/test_angles.py:361-382."""
+    saa = np.array([-120, 40., 0.04, 179.4, 94.2, 12.1], dtype=dtype)
+    vaa = np.array([60., 57.7, 175.1, 234.18, 355.4, 12.1], dtype=dtype)
+    raa = osolar.compute_relative_azimuth(vaa, saa)
+    assert raa.dtype == dtype
+    np.testing.assert_allclose(np.array([180., 17.7, 175.06, 54.78, 98.8, 0.], dtype=dtype), raa, rtol=2e-7)
+
+
+def test_observer_look_sanity():
+    """Unpinned restatement of pyorbital's get_observer_look: geometric sanity (sub-satellite point, the limb, symmetry)."""
+    t = dt.datetime(2019, 3, 14, 18)
+    az, el = osolar.get_observer_look(-75.0, 0.0, 35786.023, t, np.array([-75.0, -75.0, -65.0, -85.0, 6.3]),
+                                      np.array([0.0, 10.0, 0.0, 0.0, 0.0]), 0)
+    assert abs(el[0] - 90.0) < 1e-6                    # satellite overhead at the sub-satellite point
+    assert abs(az[1] - 180.0) < 1e-6 and 75 < el[1] < 80   # seen due south from 10 N
+    assert abs(az[2] - 270.0) < 1e-6 and abs(az[3] - 90.0) < 1e-6 and abs(el[2] - el[3]) < 1e-9
+    assert abs(el[4]) < 0.5                            # 81.3 degrees of longitude away: on the horizon
+    alt, azs = osolar.get_alt_az(dt.datetime(2022, 1, 5, 12, 50, 0), np.array([-80., 40, 0, 40, 80]), np.array([-80., 40, 0, 40, 80]))
+    assert (np.rad2deg(azs) % 360 > 0).all()           # test_angles.py:385-398
