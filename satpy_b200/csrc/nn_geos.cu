@@ -26,6 +26,27 @@
 #include "b200_geos_fast.cuh"
 
 #define GEOS_BOUND_FACTOR 0.975
+
+// Path statistics for tuning (scratch builds with -DB200_DEBUG_COUNTERS only; never in the shipped library).
+#ifdef B200_DEBUG_COUNTERS
+__device__ unsigned long long g_geos_cnt[16];
+#define GEOS_CNT(i)                                                                               \
+    do {                                                                                          \
+        unsigned m_ = __activemask();                                                             \
+        if ((int)(threadIdx.x & 31) == __ffs(m_) - 1) atomicAdd(&g_geos_cnt[i], (unsigned long long)__popc(m_)); \
+    } while (0)
+extern "C" int b200_debug_counters(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_geos_cnt, sizeof(g_geos_cnt));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_geos_cnt, z, sizeof(z));
+    }
+    return 0;
+}
+#else
+#define GEOS_CNT(i)
+#endif
 #define GEOS_POS_ERR 0.02f
 
 int b200_nn_fixed_grid_supported(const b200_geo_t *src) {
@@ -169,6 +190,7 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
     const float inf = __int_as_float(0x7f800000);
     float m1 = inf, m2 = inf;
     int i1 = -1;
+    GEOS_CNT(0);
     float4 p00 = make_float4(inf, 0.f, 0.f, 0.f), p01 = p00, p10 = p00, p11 = p00;
     {
         // the 2x2 enclosing pixels: four 128-bit loads in flight together
@@ -190,6 +212,8 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
     const float bd = fminf(G.radius_f, sqrtf(m1) + GEOS_F32_ERR);
     const float w = bd * G.inv_step * 1.0001f + GEOS_POS_ERR;
     if (w >= 1.0f) {  // else every pixel outside the 2x2 block is at least one pixel away
+        GEOS_CNT(1);
+        if (!(m1 < inf)) GEOS_CNT(8);
         const float w2 = w * w;
         const int rlo = max(0, (int)ceilf(fr - w)), rhi = min(G.H - 1, (int)floorf(fr + w));
         // Where the lattice is locally a parallelogram lattice (it is, except next to the limb), most points of that
@@ -211,14 +235,37 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
             model = (dx * dx + dy * dy + dz * dz) <= 4e-4f * fminf(gcc, grr) && det > 1e-3f * gcc * grr;
         }
         if (model) {
+            GEOS_CNT(2);
             const float d0x = txf - p00.x, d0y = tyf - p00.y, d0z = tzf - p00.z;
             const float bc = d0x * ecx + d0y * ecy + d0z * ecz, br = d0x * erx + d0y * ery + d0z * erz;
             const float inv_det = 1.0f / det;
             const float fx = (bc * grr - br * gcr) * inv_det, fy = (br * gcc - bc * gcr) * inv_det;  // model position
             const float B = 1.25f * bd + 30.0f, B2 = B * B;
-            const float hb = B * sqrtf(gcc * inv_det);
-            const int jlo = max(rlo, r0 + (int)ceilf(fy - hb)), jhi = min(rhi, r0 + (int)floorf(fy + hb));
             const float inv_gcc = 1.0f / gcc;
+            // Most targets stop here: no lattice point OUTSIDE the 2x2 block has Q < B^2, so the loop below would not
+            // examine anything.  Lower bounds of Q over the outside points: rows <= -1 and rows >= 2 through the
+            // minimum over a whole row, v^2 det / gcc; columns <= -1 and >= 2 of rows 0 and 1 through the parabola
+            // Q(., v) at the nearest admissible column (its vertex u* = -gcr v / gcc if that lies in the range).
+            const float vd = 1.0f + fy, vu = 2.0f - fy, uL = -1.0f - fx, uR = 2.0f - fx;
+            float lb = 0.0f;
+            if (vd > 0.0f && vu > 0.0f && uL < 0.0f && uR > 0.0f) {
+                const float vm = fminf(vd, vu);
+                lb = vm * vm * det * inv_gcc;
+                const float v0 = -fy, v1 = 1.0f - fy;
+                const float s0 = -gcr * v0 * inv_gcc, s1 = -gcr * v1 * inv_gcc;
+                const float g0 = grr * v0 * v0, g1 = grr * v1 * v1, h0 = 2.0f * gcr * v0, h1 = 2.0f * gcr * v1;
+                float u;
+                u = fminf(uL, s0), lb = fminf(lb, fmaf(fmaf(gcc, u, h0), u, g0));
+                u = fmaxf(uR, s0), lb = fminf(lb, fmaf(fmaf(gcc, u, h0), u, g0));
+                u = fminf(uL, s1), lb = fminf(lb, fmaf(fmaf(gcc, u, h1), u, g1));
+                u = fmaxf(uR, s1), lb = fminf(lb, fmaf(fmaf(gcc, u, h1), u, g1));
+            }
+            int jlo = 0, jhi = -1;
+            if (!(lb >= B2 * 1.0001f)) {
+                GEOS_CNT(3);
+                const float hb = B * sqrtf(gcc * inv_det);
+                jlo = max(rlo, r0 + (int)ceilf(fy - hb)), jhi = min(rhi, r0 + (int)floorf(fy + hb));
+            }
             for (int r = jlo; r <= jhi; ++r) {
                 const float b = (float)(r - r0) - fy;
                 const float disc = gcr * b * gcr * b - gcc * (grr * b * b - B2);
@@ -237,10 +284,13 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
                 const float4 *row = G.pts32 + (long long)r * G.W;
                 for (int c = clo; c <= chi; ++c) {
                     if (block_row && (c == c0 || c == c0 + 1)) continue;  // already examined
+                    GEOS_CNT(6);
                     nn_track(nn_d2f(__ldg(row + c), txf, tyf, tzf), row_base + c, m1, i1, m2);
                 }
             }
         } else {
+            GEOS_CNT(4);
+            if ((p00.x < inf) && (p01.x < inf) && (p10.x < inf) && (p11.x < inf)) GEOS_CNT(9);
             for (int r = rlo; r <= rhi; ++r) {
                 const float dr = fr - (float)r;
                 const float wc2 = w2 - dr * dr;
@@ -252,18 +302,40 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
                 const float4 *row = G.pts32 + (long long)r * G.W;
                 for (int c = clo; c <= chi; ++c) {
                     if (block_row && (c == c0 || c == c0 + 1)) continue;  // already examined
+                    GEOS_CNT(7);
                     nn_track(nn_d2f(__ldg(row + c), txf, tyf, tzf), row_base + c, m1, i1, m2);
                 }
             }
         }
     }
-    if (i1 < 0) return -1;  // no valid pixel anywhere near
+    if (i1 < 0) {
+        GEOS_CNT(10);
+        return -1;  // no valid pixel anywhere near
+    }
     const float s1 = sqrtf(m1);
     const float t = s1 + 2.0f * GEOS_F32_ERR + 0.01f;
     const bool clear_winner = m2 > t * t * 1.000001f;
     const bool clear_radius = fabsf(s1 - G.radius_f) > GEOS_F32_ERR + 0.01f;
-    if (clear_winner && clear_radius) return s1 < G.radius_f ? (long long)i1 : -1;
+    if (clear_winner && clear_radius) {
+        if (!(s1 < G.radius_f)) GEOS_CNT(11);
+        return s1 < G.radius_f ? (long long)i1 : -1;
+    }
+    GEOS_CNT(5);
     return nn_fixed_search_exact(G, fc, fr, tx, ty, tz);
+}
+
+// atan for scan angles: a full disk stays below tan = 0.16, where the odd series to x^11 is exact to float32
+// (next term x^12 / 13 < 5e-9 relative at 0.25); anything larger takes the library routine.
+__device__ __forceinline__ float nn_atan_scan(float x) {
+    if (fabsf(x) < 0.25f) {
+        const float z = x * x;
+        float p = fmaf(z, -1.0f / 11.0f, 1.0f / 9.0f);
+        p = fmaf(z, p, -1.0f / 7.0f);
+        p = fmaf(z, p, 0.2f);
+        p = fmaf(z, p, -1.0f / 3.0f);
+        return fmaf(x * z, p, x);
+    }
+    return atanf(x);
 }
 
 // target lon/lat -> fractional position in the source grid (PROJ geos forward, float32); false: far side.
@@ -275,11 +347,11 @@ __device__ __forceinline__ bool nn_fixed_position(const GeosDev &G, float rc, fl
     float tmp = G.rg - vx;
     float ax, ay;
     if (G.sweep_x) {
-        ax = atanf(vy * rsqrtf(fmaf(vz, vz, tmp * tmp)));
-        ay = atanf(__fdividef(vz, tmp));
+        ax = nn_atan_scan(vy * rsqrtf(fmaf(vz, vz, tmp * tmp)));
+        ay = nn_atan_scan(__fdividef(vz, tmp));
     } else {
-        ax = atanf(__fdividef(vy, tmp));
-        ay = atanf(vz * rsqrtf(fmaf(vy, vy, tmp * tmp)));
+        ax = nn_atan_scan(__fdividef(vy, tmp));
+        ay = nn_atan_scan(vz * rsqrtf(fmaf(vy, vy, tmp * tmp)));
     }
     fc = fmaf(ax, G.col_scale, G.col_off);
     fr = fmaf(ay, G.row_scale, G.row_off);
@@ -376,6 +448,26 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, vis);
         int64_t row_base = (int64_t)r * W;
+        if (FUSED1 && vmask == 0u) {
+            // The whole chunk is on the far side.  Its items cover one contiguous range of the output (segments
+            // tile the rows in memory order): all threads fill it with 128-bit stores.
+            int sl = seg + count - 1, rl = r;
+            while (sl >= nseg) {
+                sl -= nseg;
+                ++rl;
+            }
+            float *dst = Q.O.out + row_base + (int64_t)seg * 256;
+            const int64_t n = ((int64_t)rl * W + min(sl * 256 + 256, W)) - (row_base + (int64_t)seg * 256);
+            const int64_t head = min(n, (int64_t)(((16 - (((uintptr_t)dst) & 15)) & 15) >> 2));
+            if ((int64_t)threadIdx.x < head) st_stream_f1(dst + threadIdx.x, Q.O.fill);
+            const int64_t nvec = (n - head) >> 2;
+            float *body = dst + head;
+            for (int64_t j = threadIdx.x; j < nvec; j += 256)
+                st_stream_f4(body + 4 * j, Q.O.fill, Q.O.fill, Q.O.fill, Q.O.fill);
+            const int64_t tail = head + 4 * nvec;
+            if (tail + (int64_t)threadIdx.x < n) st_stream_f1(dst + tail + threadIdx.x, Q.O.fill);
+            continue;
+        }
         for (int k = 0; k < count; ++k, ++seg) {
             if (seg == nseg) {
                 seg = 0;

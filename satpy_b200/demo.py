@@ -101,14 +101,17 @@ def seviri_bt(shape, seed: int = 1) -> np.ndarray:
     return rng.uniform(200.0, 320.0, size=shape).astype(np.float32)
 
 
-def viirs_like_swath(nscans=12, rows_per_scan=16, ncols=400, dtype=np.float32, bowtie=0.0):
+def viirs_like_swath(nscans=12, rows_per_scan=16, ncols=400, dtype=np.float32, bowtie=0.0, lat0=70.0, lat_span=6.0,
+                     lon_half_width=9.0):
     """Config 4 stand-in: a smooth high-latitude swath of ``nscans * rows_per_scan`` rows (M-band geometry in
-    miniature: 16 rows per scan); ``bowtie > 0`` makes consecutive scans overlap towards the swath edges."""
+    miniature: 16 rows per scan); ``bowtie > 0`` makes consecutive scans overlap towards the swath edges.
+    ``lat0=28, lat_span=51.8, lon_half_width=10.79`` with 480 scans x 3200 columns gives the real 750 m M-band
+    sampling of ten granules (scripts/kernel_bench.py)."""
     nrows = nscans * rows_per_scan
     scan = (np.arange(nrows) // rows_per_scan)[:, None].astype(np.float64)
     within = ((np.arange(nrows) % rows_per_scan)[:, None] - (rows_per_scan - 1) / 2.0) / rows_per_scan
     xt = np.linspace(-1.0, 1.0, ncols)[None, :]
     at = (scan + 0.5 + within * (1.0 + bowtie * xt * xt)) / nscans
-    lat = 70.0 + 6.0 * at + 0.25 * xt
-    lon = -20.0 + 9.0 * xt / np.cos(np.deg2rad(lat)) + 4.0 * at
+    lat = lat0 + lat_span * at + 0.25 * xt
+    lon = -20.0 + lon_half_width * xt / np.cos(np.deg2rad(lat)) + 4.0 * at
     return lon.astype(dtype), lat.astype(dtype), rows_per_scan

@@ -325,7 +325,7 @@ class SwathDefinition(BaseDefinition):
     """Explicit lon/lat arrays (degrees), numpy or torch, float32 or float64."""
 
     def __init__(self, lons, lats):
-        if hasattr(lons, "values"):  # xarray.DataArray
+        if hasattr(lons, "dims") and hasattr(lons, "values"):  # xarray.DataArray (torch tensors have .values() too)
             lons, lats = lons.values, lats.values
         self.lons = lons
         self.lats = lats

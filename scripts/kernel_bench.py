@@ -135,11 +135,13 @@ def main():
     rec("bil_sample_f32_kernel", "C3 sample 36 Mpix", ms, 36 * d3.size)
     del rb, ahi
 
-    # ---- config 4: VIIRS M-band-like swath 7680 x 3200, EWA to a 750 m polar stereographic grid
-    lon, lat, rps = demo.viirs_like_swath(nscans=480, rows_per_scan=16, ncols=3200)
-    swath = SwathDefinition(lon, lat)
+    # ---- config 4: ten VIIRS M-band granules' worth of swath (7680 x 3200 at the real 750 m sampling) to a 750 m
+    # polar-stereographic grid: EWA, and nearest neighbour through the general (bucket) search engine
+    lon, lat, rps = demo.viirs_like_swath(nscans=480, rows_per_scan=16, ncols=3200, lat0=28.0, lat_span=51.8,
+                                          lon_half_width=10.79)
+    swath = SwathDefinition(torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda())
     d4 = AreaDefinition("ps", "ps", "ps", {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 0.0, "ellps": "WGS84"},
-                        4400, 4400, (-1.5e6, -2.7e6, 1.8e6, 0.6e6))
+                        6400, 9200, (-3.95e6, -7.1e6, 0.85e6, -0.2e6))
     re = B200EWAResampler(swath, d4)
     ms = timeit(lambda: (setattr(re, "_cr", None), re.precompute()), steps=3, warmup=1)
     rec("ll2cr_kernel<float>", "C4 swath 7680x3200 -> (col, row)", ms, 16 * swath.size)
@@ -147,6 +149,17 @@ def main():
     ms = timeit(lambda: re.compute(sw, rows_per_scan=rps), steps=3, warmup=1)
     rec("fornav (params + accumulate + finalize)", f"C4 EWA 24.6 Mpix swath -> {d4.width}x{d4.height} grid, "
         f"{re.valid_counts[0]} cells filled", ms, 12 * swath.size + 12 * d4.size, "float32 atomics into L2")
+    del re
+    for radius in (2000.0, 5000.0):
+        rn = B200NearestResampler(swath, d4)
+        ms = timeit(lambda: (rn._index_caches.clear(), rn.precompute(radius_of_influence=radius)), steps=3, warmup=1)
+        hits = float((rn._current["gather_index"] >= 0).float().mean())
+        rec("nn_grid_create + nn_query (bucket engine)", f"C4 nearest: 24.6 Mpix swath -> {d4.width}x{d4.height} grid, "
+            f"r={radius:.0f} m, {hits:.3f} of the grid hit", ms, 24 * swath.size + 4 * d4.size,
+            "xyz build + counting sort + query; index array out")
+        ms = timeit(lambda: rn.compute(sw, fill_value=float("nan")), steps=3, warmup=1)
+        rec("nn_gather_kernel<float>", "C4 gather", ms, 8 * d4.size + 4 * swath.size)
+        del rn
     if args.out:
         with open(args.out, "w") as fh:
             json.dump({"peak_hbm_gbs": pk, "rows": rows}, fh, indent=1)

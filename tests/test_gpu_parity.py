@@ -467,6 +467,22 @@ def test_nearest_float32_swath_and_empty_results():
         r.compute(np.ones((3, 3), np.float32))
 
 
+def test_swath_lonlats_may_be_device_tensors():
+    """A swath whose lon/lat already live in HBM (what a device reader hands over) gives the result of the same
+    swath passed as numpy arrays."""
+    import torch
+    lon, lat, _ = demo.viirs_like_swath(nscans=10, ncols=300)
+    data = np.random.default_rng(3).uniform(0, 1, lon.shape).astype(np.float32)
+    dst = AreaDefinition("ps", "ps", "ps", {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 0.0,
+                                            "ellps": "WGS84"}, 240, 200, (-1.6e6, -2.4e6, 0.2e6, -0.9e6))
+    on_host = B200NearestResampler(SwathDefinition(lon, lat), dst).resample(data, radius_of_influence=8000.0)
+    dev = SwathDefinition(torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda())
+    assert dev.shape == lon.shape
+    on_dev = B200NearestResampler(dev, dst).resample(torch.from_numpy(data).cuda(), radius_of_influence=8000.0)
+    np.testing.assert_array_equal(on_dev.cpu().numpy(), on_host)
+    assert np.isfinite(on_host).sum() > 500
+
+
 # ------------------------------------------------------------------------------------ pipeline
 def test_pipeline_matches_oracle_and_cached_mode():
     import torch
