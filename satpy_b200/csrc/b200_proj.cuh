@@ -28,14 +28,29 @@ __device__ __forceinline__ double b200_tsfn(double phi, double sinphi, double e)
     return tan(0.5 * (B200_HALFPI - phi)) / pow((1.0 - con) / (1.0 + con), 0.5 * e);
 }
 
+// Latitude from the conformal quantity ts (PROJ pj_phi2).  PROJ iterates phi <- pi/2 - 2 atan(ts ((1 - e sin phi) /
+// (1 + e sin phi))^(e/2)) from the conformal latitude chi; each pass gains a factor ~e^2, six passes to 1e-13.  The
+// same fixed-point iteration is run here to the same tolerance, but started from the series
+// phi = chi + c2 sin 2chi + c4 sin 4chi + c6 sin 6chi + c8 sin 8chi (coefficients through e^8, error < 3e-12 rad), so two
+// passes suffice; the converged value agrees with the plain iteration to the last bit or two (4e-16 rad).
 __device__ __forceinline__ double b200_phi2(double ts, double e) {
-    double eccnth = 0.5 * e;
-    double phi = B200_HALFPI - 2.0 * atan(ts);
+    const double eccnth = 0.5 * e;
+    const double chi = B200_HALFPI - 2.0 * atan(ts);
+    const double es = e * e, es2 = es * es, es3 = es2 * es, es4 = es2 * es2;
+    const double c2 = es / 2.0 + 5.0 * es2 / 24.0 + es3 / 12.0 + 13.0 * es4 / 360.0;
+    const double c4 = 7.0 * es2 / 48.0 + 29.0 * es3 / 240.0 + 811.0 * es4 / 11520.0;
+    const double c6 = 7.0 * es3 / 120.0 + 81.0 * es4 / 1120.0;
+    const double c8 = 4279.0 * es4 / 161280.0;
+    double s1, k1;
+    sincos(chi, &s1, &k1);
+    const double s2 = 2.0 * s1 * k1, k2 = 1.0 - 2.0 * s1 * s1;
+    const double s4 = 2.0 * s2 * k2, k4 = 1.0 - 2.0 * s2 * s2;
+    double phi = chi + c2 * s2 + c4 * s4 + c6 * (s2 * k4 + k2 * s4) + c8 * (2.0 * s4 * k4);
     for (int i = 0; i < 15; ++i) {
         double con = e * sin(phi);
         double dphi = B200_HALFPI - 2.0 * atan(ts * pow((1.0 - con) / (1.0 + con), eccnth)) - phi;
         phi += dphi;
-        if (fabs(dphi) <= 1e-13) break;  // tighter than PROJ's 1e-10: matches the oracle's run-to-all-converged loop
+        if (fabs(dphi) <= 1e-13) break;
     }
     return phi;
 }

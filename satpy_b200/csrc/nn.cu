@@ -12,27 +12,31 @@
 //
 // Two exact engines stand in for the kd-tree; both break exact float64 distance ties towards the lowest
 // source index, so they return identical indices:
-//   * bucket grid (this file; any source, swath or area): latitude bands of height >= the search cap
-//     angle, each band cut into ~square longitude cells; cells of a band are contiguous, and the valid
-//     source points are counting-sorted by cell into one array of 32-byte records {x, y, z, raw index}.
-//     A query turns the spherical cap of the search radius into (bands) x (one or two contiguous cell
-//     ranges per band), i.e. a handful of contiguous record ranges that it scans with 128-bit loads.
+//   * bucket grid (this file; any source, swath or area): latitude bands over the source's latitude range,
+//     each band cut into ~square longitude cells sized to hold a few source points (from a sampled estimate
+//     of the point density); cells of a band are contiguous, and the valid source points are counting-sorted
+//     by cell into one array of 32-byte records {x, y, z, raw index}.  A query turns a spherical cap into
+//     (bands) x (one or two contiguous cell ranges per band), i.e. a handful of contiguous record ranges
+//     that it scans with 128-bit loads -- first the cap of ONE cell size, which already holds the answer
+//     wherever the source is dense, and only then the cap of the full radius of influence.
 //   * fixed grid (nn_geos.cu; geostationary area sources): the source grid itself is the index.
 // Targets whose lon depends on the column only and lat on the row only (longlat / eqc / merc) get
 // per-column and per-row tables so that no transcendental is evaluated per pixel.
+#include <climits>
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include "nn_common.cuh"
 #include "b200_geos_fast.cuh"
 
 #define B200_NN_MAX_CELLS (160LL * 1000 * 1000)
+#define B200_NN_CELL_POINTS 4.0  /* source points per cell the layout aims for */
 
 struct GridDev {
     const int32_t *band_off;
     const int32_t *cell_start;
     const double4 *pts;
     const int32_t *prefix;
-    double inv_dphi;
+    double inv_dphi, phi0;
     int32_t nbands;
 };
 
@@ -40,14 +44,16 @@ struct SrcArg {
     b200_geo_t g;
 };
 
-__device__ __forceinline__ int b200_band_of(double phi, double inv_dphi, int nbands) {
-    int b = (int)floor((phi + B200_HALFPI) * inv_dphi);
-    return min(nbands - 1, max(0, b));
+// latitudes below / above the banded range belong to the first / last band (monotone, so a cap [phi - t, phi + t]
+// always maps to a band range that contains every point inside it)
+__device__ __forceinline__ int b200_band_of(double phi, double phi0, double inv_dphi, int nbands) {
+    double b = floor((phi - phi0) * inv_dphi);
+    return (int)fmin((double)(nbands - 1), fmax(0.0, b));
 }
 
-__device__ __forceinline__ int b200_cell_of(const int32_t *__restrict__ band_off, double lam, double phi,
+__device__ __forceinline__ int b200_cell_of(const int32_t *__restrict__ band_off, double lam, double phi, double phi0,
                                             double inv_dphi, int nbands) {
-    int b = b200_band_of(phi, inv_dphi, nbands);
+    int b = b200_band_of(phi, phi0, inv_dphi, nbands);
     int off = __ldg(band_off + b);
     int nb = __ldg(band_off + b + 1) - off;
     int c = (int)floor((lam + B200_PI) * ((double)nb / B200_TWO_PI));
@@ -61,7 +67,7 @@ __device__ __forceinline__ int b200_cell_of(const int32_t *__restrict__ band_off
 __global__ void __launch_bounds__(256)
 nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask,
                         uint8_t *__restrict__ valid_input, double4 *__restrict__ rec, float4 *__restrict__ rec32,
-                        int32_t *__restrict__ cell_of, const int32_t *__restrict__ band_off, double inv_dphi,
+                        int32_t *__restrict__ cell_of, const int32_t *__restrict__ band_off, double phi0, double inv_dphi,
                         int nbands, const __grid_constant__ GeosFast F) {
     const int64_t W = S.g.width;
     const int64_t n = S.g.nrows * W;
@@ -93,7 +99,7 @@ nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restr
         p[1] = make_double2(z, __longlong_as_double((long long)i));
         if (rec32) rec32[i] = ok ? make_float4((float)x, (float)y, (float)z, 0.0f)
                                  : make_float4(__int_as_float(0x7f800000), 0.0f, 0.0f, 0.0f);
-        if (cell_of) cell_of[i] = ok ? b200_cell_of(band_off, lam, phi, inv_dphi, nbands) : -1;
+        if (cell_of) cell_of[i] = ok ? b200_cell_of(band_off, lam, phi, phi0, inv_dphi, nbands) : -1;
     }
 }
 
@@ -119,6 +125,61 @@ nn_cell_scatter_kernel(const int32_t *__restrict__ cell_of, const double4 *__res
         double2 *p = reinterpret_cast<double2 *>(pts + slot);
         p[0] = q[0];
         p[1] = q[1];
+    }
+}
+
+// Density and latitude range of the source from a regular sample of its pixels (at most NN_STATS_SIDE^2): the mean
+// area per pixel (|step to the right| x |step down|) sizes the cells, the latitude range places the bands.  Both only
+// tune the layout -- a point outside the sampled range lands in an edge band and is still found.
+#define NN_STATS_SIDE 512
+struct SrcStats {
+    double area_sum;
+    unsigned long long pairs;
+    long long phi_min_k, phi_max_k;  // fixed point, 1e-12 rad
+};
+
+__device__ __forceinline__ bool nn_stats_point(const SrcArg &S, const uint8_t *__restrict__ mask, int64_t r, int64_t c,
+                                               double &x, double &y, double &z, double &phi) {
+    if (r >= S.g.nrows || c >= S.g.width) return false;
+    if (mask != nullptr && mask[r * S.g.width + c]) return false;
+    double lon, lat, lam;
+    b200_geo_lonlat(S.g, S.g.row0 + r, c, lon, lat);
+    if (!b200_lonlat_valid(lon, lat)) return false;
+    b200_lonlat2xyz(lon, lat, x, y, z, lam, phi);
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+nn_source_stats_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask, int rs, int cs,
+                       SrcStats *__restrict__ st) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double area = 0.0;
+    unsigned long long pairs = 0;
+    long long kmin = LLONG_MAX, kmax = LLONG_MIN;
+    if (t < rs * cs) {
+        const int64_t r = (int64_t)(t / cs) * S.g.nrows / rs, c = (int64_t)(t % cs) * S.g.width / cs;
+        double x, y, z, phi, x1, y1, z1, x2, y2, z2, p_;
+        if (nn_stats_point(S, mask, r, c, x, y, z, phi)) {
+            kmin = kmax = llrint(phi * 1e12);
+            if (nn_stats_point(S, mask, r, c + 1, x1, y1, z1, p_) && nn_stats_point(S, mask, r + 1, c, x2, y2, z2, p_)) {
+                area = sqrt(b200_nn_d2(x1, y1, z1, x, y, z) * b200_nn_d2(x2, y2, z2, x, y, z));
+                pairs = 1;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        area += __shfl_xor_sync(0xffffffffu, area, o);
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+        atomicMin(&st->phi_min_k, kmin);
+        atomicMax(&st->phi_max_k, kmax);
+        if (pairs) {
+            atomicAdd(&st->area_sum, area);
+            atomicAdd(&st->pairs, pairs);
+        }
     }
 }
 
@@ -189,34 +250,59 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
     const int64_t n_src = g->n_src;
     int32_t *counts = nullptr, *cell_of = nullptr, *h_off = nullptr;
     double4 *rec = nullptr;
+    SrcStats *d_st = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
     int64_t ncells = 0;
     int nbands = 1;
-    double inv_dphi = 1.0;
+    double inv_dphi = 1.0, phi0 = -B200_HALFPI;
     SrcArg S;
     S.g = *src;
     GeosFast fast;
     memset(&fast, 0, sizeof(fast));
     b200_pool_keep_memory();
     if (bucket) {
-        // ---- host: band layout.  Band height >= cap angle; widened if the table would get too large.
-        double dphi = b200_cap_angle(g->radius);
-        double min_dphi = sqrt(4.0 * B200_PI / (double)B200_NN_MAX_CELLS);
-        if (dphi < min_dphi) dphi = min_dphi;
+        // ---- cell size from the sampled point density, bands over the sampled latitude range
+        SrcStats h_st;
+        h_st.area_sum = 0.0;
+        h_st.pairs = 0;
+        h_st.phi_min_k = LLONG_MAX;
+        h_st.phi_max_k = LLONG_MIN;
+        const int rs = (int)(src->nrows < NN_STATS_SIDE ? src->nrows : NN_STATS_SIDE);
+        const int cs = (int)(src->width < NN_STATS_SIDE ? src->width : NN_STATS_SIDE);
+        NN_TRY(cudaMallocAsync((void **)&d_st, sizeof(SrcStats), s));
+        NN_TRY(cudaMemcpyAsync(d_st, &h_st, sizeof(SrcStats), cudaMemcpyHostToDevice, s));
+        nn_source_stats_kernel<<<(rs * cs + 255) / 256, 256, 0, s>>>(S, mask, rs, cs, d_st);
+        NN_TRY(cudaGetLastError());
+        NN_TRY(cudaMemcpyAsync(&h_st, d_st, sizeof(SrcStats), cudaMemcpyDeviceToHost, s));
+        NN_TRY(cudaStreamSynchronize(s));
+        cudaFreeAsync(d_st, s);
+        d_st = nullptr;
+        double dphi = b200_cap_angle(g->radius);  // no usable sample: one cell per search cap
+        if (h_st.pairs >= 16 && h_st.area_sum > 0.0)
+            dphi = sqrt(B200_NN_CELL_POINTS * h_st.area_sum / (double)h_st.pairs) / B200_R_EARTH;
+        if (!(dphi > 1e-9)) dphi = 1e-9;
         if (dphi > B200_PI) dphi = B200_PI;
-        nbands = (int)ceil(B200_PI / dphi);
+        double lo = -B200_HALFPI, hi = B200_HALFPI;
+        if (h_st.phi_min_k <= h_st.phi_max_k) {
+            lo = fmax(lo, (double)h_st.phi_min_k * 1e-12 - 2.0 * dphi);
+            hi = fmin(hi, (double)h_st.phi_max_k * 1e-12 + 2.0 * dphi);
+        }
+        // cells are ~dphi x dphi: keep the table below B200_NN_MAX_CELLS
+        const double zone = B200_TWO_PI * fmax(sin(hi) - sin(lo), 1e-12);
+        if (zone / (dphi * dphi) > (double)B200_NN_MAX_CELLS) dphi = sqrt(zone / (double)B200_NN_MAX_CELLS);
+        nbands = (int)ceil((hi - lo) / dphi);
         if (nbands < 1) nbands = 1;
         inv_dphi = 1.0 / dphi;
+        phi0 = lo;
         h_off = new (std::nothrow) int32_t[nbands + 1];
         if (!h_off) {
             b200_set_error("b200_nn_grid_create: out of host memory");
             return B200_ENOMEM;
         }
         for (int b = 0; b < nbands; ++b) {
-            double lo = -B200_HALFPI + b * dphi, hi = lo + dphi;
-            if (hi > B200_HALFPI) hi = B200_HALFPI;
-            double cmax = (lo <= 0.0 && hi >= 0.0) ? 1.0 : fmax(cos(lo), cos(hi));
+            double blo = lo + b * dphi, bhi = fmin(blo + dphi, B200_HALFPI);
+            double cmax = (blo <= 0.0 && bhi >= 0.0) ? 1.0 : fmax(cos(blo), cos(bhi));
             int64_t nb = (int64_t)floor(B200_TWO_PI * cmax / dphi);
             if (nb < 1) nb = 1;
             h_off[b] = (int32_t)ncells;
@@ -226,6 +312,7 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
         g->ncells = ncells;
         g->nbands = nbands;
         g->dphi = dphi;
+        g->phi0 = phi0;
         NN_TRY(cudaMallocAsync((void **)&g->band_off, (size_t)(nbands + 1) * sizeof(int32_t), s));
         NN_TRY(cudaMemcpyAsync(g->band_off, h_off, (size_t)(nbands + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         NN_TRY(cudaStreamSynchronize(s));  // h_off is pageable: finish before freeing it
@@ -236,7 +323,7 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
     rc = b200_geos_fast_prepare(src, &fast, s);
     if (rc) goto fail;
     nn_source_points_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, mask, valid_input, rec, g->pts32, cell_of,
-                                                                        g->band_off, inv_dphi, nbands, fast);
+                                                                        g->band_off, phi0, inv_dphi, nbands, fast);
     NN_TRY(cudaGetLastError());
     b200_geos_fast_release(&fast, s);
     rc = nn_prefix(g, valid_input, s);
@@ -269,6 +356,7 @@ fail:
     if (counts) cudaFreeAsync(counts, s);
     if (cell_of) cudaFreeAsync(cell_of, s);
     if (rec) cudaFreeAsync(rec, s);
+    if (d_st) cudaFreeAsync(d_st, s);
     if (tmp) cudaFreeAsync(tmp, s);
     return rc;
 }
@@ -341,12 +429,9 @@ __device__ __forceinline__ double nn_cap_dlam(double phi, double theta, double s
     return asin(q) * (1.0 + 1e-12) + 1e-12;
 }
 
-// nearest valid source point of one target given its spherical coordinates; -1 when none within the radius
-__device__ __forceinline__ long long nn_bucket_point(const GridDev &G, double lam, double tx, double ty, double tz,
-                                                     int b_lo, int b_hi, double dlam, double r2) {
-    Best best;
-    best.d2 = r2;  // strict "<": a neighbour exactly at the radius is not accepted
-    best.idx = -1;
+// scan every record of the cells that meet the cap (bands b_lo..b_hi, longitudes lam +- dlam)
+__device__ __forceinline__ void nn_bucket_scan(const GridDev &G, double lam, double tx, double ty, double tz, int b_lo,
+                                               int b_hi, double dlam, Best &best) {
     const bool full = dlam >= B200_PI;
     for (int b = b_lo; b <= b_hi; ++b) {
         int off = __ldg(G.band_off + b);
@@ -368,6 +453,28 @@ __device__ __forceinline__ long long nn_bucket_point(const GridDev &G, double la
         }
         nn_scan_range(G.pts, __ldg(G.cell_start + off + c0), __ldg(G.cell_start + off + c1 + 1), tx, ty, tz, best);
     }
+}
+
+// Search caps of one target: the full radius of influence and, when cells are much smaller than that, a first cap of
+// one cell size (radius r1).
+struct Caps {
+    int b_lo, b_hi, b_lo1, b_hi1;
+    double dlam, dlam1;
+};
+
+// nearest valid source point of one target given its spherical coordinates; -1 when none within the radius.
+// The first cap covers every point closer than r1: a hit closer than r1 in it is the overall nearest (everything
+// not scanned is at least r1 away), which settles the targets inside a dense source after a few records.
+__device__ __forceinline__ long long nn_bucket_point(const GridDev &G, double lam, double tx, double ty, double tz,
+                                                     const Caps &C, double r2, double r1_2) {
+    Best best;
+    best.d2 = r2;  // strict "<": a neighbour exactly at the radius is not accepted
+    best.idx = -1;
+    if (r1_2 > 0.0) {
+        nn_bucket_scan(G, lam, tx, ty, tz, C.b_lo1, C.b_hi1, C.dlam1, best);
+        if (best.d2 < r1_2) return best.idx;
+    }
+    nn_bucket_scan(G, lam, tx, ty, tz, C.b_lo, C.b_hi, C.dlam, best);
     return best.idx;
 }
 
@@ -376,6 +483,7 @@ struct QueryArg {
     GridDev G;
     QueryOut O;
     double theta, sin_theta, r2;
+    double theta1, sin_theta1, r1_2;  // first cap; r1_2 = 0: single phase
     const TgtCol *cols;  // rectilinear targets only
     const TgtRow *rows;
 };
@@ -394,9 +502,18 @@ __global__ void __launch_bounds__(256) nn_bucket_query_kernel(const __grid_const
         if (ok) {
             double tx, ty, tz, lam, phi;
             b200_lonlat2xyz(lon, lat, tx, ty, tz, lam, phi);
-            int b_lo = b200_band_of(phi - Q.theta, Q.G.inv_dphi, Q.G.nbands);
-            int b_hi = b200_band_of(phi + Q.theta, Q.G.inv_dphi, Q.G.nbands);
-            raw = nn_bucket_point(Q.G, lam, tx, ty, tz, b_lo, b_hi, nn_cap_dlam(phi, Q.theta, Q.sin_theta), Q.r2);
+            Caps C;
+            C.b_lo = b200_band_of(phi - Q.theta, Q.G.phi0, Q.G.inv_dphi, Q.G.nbands);
+            C.b_hi = b200_band_of(phi + Q.theta, Q.G.phi0, Q.G.inv_dphi, Q.G.nbands);
+            C.dlam = nn_cap_dlam(phi, Q.theta, Q.sin_theta);
+            C.b_lo1 = C.b_hi1 = 0;
+            C.dlam1 = 0.0;
+            if (Q.r1_2 > 0.0) {
+                C.b_lo1 = b200_band_of(phi - Q.theta1, Q.G.phi0, Q.G.inv_dphi, Q.G.nbands);
+                C.b_hi1 = b200_band_of(phi + Q.theta1, Q.G.phi0, Q.G.inv_dphi, Q.G.nbands);
+                C.dlam1 = nn_cap_dlam(phi, Q.theta1, Q.sin_theta1);
+            }
+            raw = nn_bucket_point(Q.G, lam, tx, ty, tz, C, Q.r2, Q.r1_2);
         }
         b200_nn_emit(Q.O, Q.G.prefix, i, raw, ok);
     }
@@ -419,7 +536,14 @@ __global__ void __launch_bounds__(256) nn_bucket_query_rect_kernel(const __grid_
             double tx = B200_R_EARTH * R.cos_phi * Cc.cos_lam;
             double ty = B200_R_EARTH * R.cos_phi * Cc.sin_lam;
             double tz = B200_R_EARTH * R.sin_phi;
-            raw = nn_bucket_point(Q.G, Cc.lam, tx, ty, tz, R.b_lo, R.b_hi, R.dlam, Q.r2);
+            Caps C;
+            C.b_lo = R.b_lo;
+            C.b_hi = R.b_hi;
+            C.dlam = R.dlam;
+            C.b_lo1 = R.b_1 & 0xffffff;
+            C.b_hi1 = C.b_lo1 + (int)((unsigned)R.b_1 >> 24);
+            C.dlam1 = R.dlam1;
+            raw = nn_bucket_point(Q.G, Cc.lam, tx, ty, tz, C, Q.r2, Q.r1_2);
         }
         b200_nn_emit(Q.O, Q.G.prefix, (int64_t)r * W + col, raw, ok);
     }
@@ -429,6 +553,7 @@ __global__ void __launch_bounds__(256) nn_bucket_query_rect_kernel(const __grid_
 struct TableArg {
     b200_geo_t dst;
     double theta, sin_theta, inv_dphi;  // bucket mode
+    double theta1, sin_theta1, phi0;    // ... first cap (theta1 = 0: none), lower edge of band 0
     int32_t nbands, geos;
     double lam0;                        // fixed-grid mode: geos source constants
     double rp, rp2;
@@ -459,8 +584,8 @@ nn_target_tables_kernel(const __grid_constant__ TableArg A, TgtCol *__restrict__
             t.phi = lat * B200_DEG2RAD;
             sincos(t.phi, &t.sin_phi, &t.cos_phi);
             t.valid = (lat >= -90.0 && lat <= 90.0) ? 1 : 0;
-            t.dlam = 0.0;
-            t.b_lo = t.b_hi = 0;
+            t.dlam = t.dlam1 = 0.0;
+            t.b_lo = t.b_hi = t.b_1 = 0;
             t.rc = t.rs = 0.0f;
             if (t.valid) {
                 if (A.geos) {
@@ -471,19 +596,23 @@ nn_target_tables_kernel(const __grid_constant__ TableArg A, TgtCol *__restrict__
                     t.rs = (float)(rr * sin(pg));
                 } else {
                     t.dlam = nn_cap_dlam(t.phi, A.theta, A.sin_theta);
-                    t.b_lo = b200_band_of(t.phi - A.theta, A.inv_dphi, A.nbands);
-                    t.b_hi = b200_band_of(t.phi + A.theta, A.inv_dphi, A.nbands);
+                    t.b_lo = b200_band_of(t.phi - A.theta, A.phi0, A.inv_dphi, A.nbands);
+                    t.b_hi = b200_band_of(t.phi + A.theta, A.phi0, A.inv_dphi, A.nbands);
+                    if (A.theta1 > 0.0) {
+                        const int lo1 = b200_band_of(t.phi - A.theta1, A.phi0, A.inv_dphi, A.nbands);
+                        const int hi1 = b200_band_of(t.phi + A.theta1, A.phi0, A.inv_dphi, A.nbands);
+                        t.b_1 = lo1 | ((hi1 - lo1) << 24);
+                        t.dlam1 = nn_cap_dlam(t.phi, A.theta1, A.sin_theta1);
+                    }
                 }
             }
-            t.pad = 0;
-            t.pad2 = 0.0;
             rows[r] = t;
         }
     }
 }
 
-int b200_nn_build_tables(const b200_geo_t *dst, double theta, double inv_dphi, int nbands, int geos, double lam0,
-                         double rp, double rp2, TgtCol **cols, TgtRow **rows, cudaStream_t s) {
+int b200_nn_build_tables(const b200_geo_t *dst, double theta, double theta1, double phi0, double inv_dphi, int nbands,
+                         int geos, double lam0, double rp, double rp2, TgtCol **cols, TgtRow **rows, cudaStream_t s) {
     *cols = nullptr;
     *rows = nullptr;
     B200_CUDA(cudaMallocAsync((void **)cols, (size_t)dst->width * sizeof(TgtCol), s));
@@ -497,6 +626,9 @@ int b200_nn_build_tables(const b200_geo_t *dst, double theta, double inv_dphi, i
     A.dst = *dst;
     A.theta = theta;
     A.sin_theta = theta >= B200_HALFPI ? 1.0 : sin(theta);
+    A.theta1 = theta1;
+    A.sin_theta1 = theta1 >= B200_HALFPI ? 1.0 : sin(theta1);
+    A.phi0 = phi0;
     A.inv_dphi = inv_dphi;
     A.nbands = nbands;
     A.geos = geos;
@@ -517,18 +649,28 @@ static int nn_bucket_query(const b200_nn_grid *grid, const b200_geo_t *dst, doub
     Q.G.pts = grid->pts;
     Q.G.prefix = grid->prefix;
     Q.G.inv_dphi = 1.0 / grid->dphi;
+    Q.G.phi0 = grid->phi0;
     Q.G.nbands = grid->nbands;
     Q.O = O;
     Q.theta = b200_cap_angle(radius);
     Q.sin_theta = Q.theta >= B200_HALFPI ? 1.0 : sin(Q.theta);
     Q.r2 = radius * radius;
+    // first cap: one cell size, when that is well below the radius of influence (and the band span fits the tables)
+    const double r1 = grid->dphi * B200_R_EARTH;
+    Q.theta1 = Q.sin_theta1 = Q.r1_2 = 0.0;
+    if (r1 < 0.6 * radius) {
+        Q.theta1 = b200_cap_angle(r1);
+        Q.sin_theta1 = sin(Q.theta1);
+        Q.r1_2 = r1 * r1;
+    }
     Q.cols = nullptr;
     Q.rows = nullptr;
     const int64_t n = dst->nrows * dst->width;
     if (b200_geo_is_rectilinear(dst) && dst->width < (1LL << 30)) {
         TgtCol *cols;
         TgtRow *rows;
-        int rc = b200_nn_build_tables(dst, Q.theta, Q.G.inv_dphi, Q.G.nbands, 0, 0.0, 0.0, 0.0, &cols, &rows, s);
+        int rc = b200_nn_build_tables(dst, Q.theta, Q.theta1, Q.G.phi0, Q.G.inv_dphi, Q.G.nbands, 0, 0.0, 0.0, 0.0, &cols,
+                                      &rows, s);
         if (rc) return rc;
         Q.cols = cols;
         Q.rows = rows;

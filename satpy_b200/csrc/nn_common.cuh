@@ -28,7 +28,8 @@ struct b200_nn_grid {
     // ---- bucket mode
     int64_t ncells;
     int32_t nbands;
-    double dphi;
+    double dphi;          // band height = cell size (radians): a few source points per cell, independent of the radius
+    double phi0;          // lower edge of band 0; latitudes outside [phi0, phi0 + nbands * dphi) go to the edge bands
     int32_t *band_off;    // [nbands + 1] first cell of each band
     int32_t *cell_start;  // [ncells + 1] first record of each cell
     // ---- fixed-grid mode: the source area itself is the index
@@ -47,8 +48,9 @@ struct TgtRow {  // 64 B
     double phi, sin_phi, cos_phi;
     double dlam;       // longitude half-width of the search cap at this latitude (bucket mode); >= pi: whole circle
     float rc, rs;      // geos source: r*cos(pg), r*sin(pg) of the geocentric latitude (fixed-grid mode)
-    int32_t valid, b_lo, b_hi, pad;
-    double pad2;
+    int32_t valid, b_lo, b_hi;
+    int32_t b_1;       // bucket mode, first phase (one-cell cap): b_lo1 | (b_hi1 - b_lo1) << 24
+    double dlam1;      // ... and its longitude half-width
 };
 
 // lon depends on the column only and lat on the row only
@@ -127,8 +129,8 @@ static inline double b200_cap_angle(double radius) {
 }
 
 // implemented in nn.cu
-int b200_nn_build_tables(const b200_geo_t *dst, double theta, double inv_dphi, int nbands, int geos, double lam0,
-                         double rp, double rp2, TgtCol **cols, TgtRow **rows, cudaStream_t s);
+int b200_nn_build_tables(const b200_geo_t *dst, double theta, double theta1, double phi0, double inv_dphi, int nbands,
+                         int geos, double lam0, double rp, double rp2, TgtCol **cols, TgtRow **rows, cudaStream_t s);
 
 // implemented in nn_geos.cu
 int b200_nn_fixed_grid_supported(const b200_geo_t *src);

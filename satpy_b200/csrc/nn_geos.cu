@@ -564,7 +564,7 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
     if (b200_geo_is_rectilinear(dst) && dst->width < (1LL << 30)) {
         TgtCol *cols;
         TgtRow *rows;
-        int rc = b200_nn_build_tables(dst, 0.0, 1.0, 1, 1, P.lam0, P.p[3], P.p[4], &cols, &rows, s);
+        int rc = b200_nn_build_tables(dst, 0.0, 0.0, 0.0, 1.0, 1, 1, P.lam0, P.p[3], P.p[4], &cols, &rows, s);
         if (rc) return rc;
         Q.cols = cols;
         Q.rows = rows;
