@@ -467,6 +467,34 @@ def test_nearest_float32_swath_and_empty_results():
         r.compute(np.ones((3, 3), np.float32))
 
 
+@pytest.mark.parametrize("radius", [12000.0, 60000.0])
+def test_bucket_search_first_cap_holes_and_stray_rows(radius):
+    """The bucket engine sizes its cells from a SAMPLE of the source and scans a one-cell cap before the full radius.
+    Neither may change a result: targets next to masked holes have their nearest neighbour beyond the first cap, and a
+    scan line far outside the sampled latitude range (row 6 is not in the 512-row sample of 600 rows) still has to
+    be found through the edge band."""
+    h, w = 600, 520
+    rng = np.random.default_rng(21)
+    lat = np.linspace(44.0, 62.0, h)[:, None] + 0.3 * np.linspace(-1, 1, w)[None, :] ** 2
+    lon = np.linspace(-8.0, 22.0, w)[None, :] + 0.02 * np.arange(h)[:, None]
+    lat = lat + rng.uniform(-0.002, 0.002, (h, w))
+    lat[6, :] = 71.5 + 0.01 * np.sin(np.arange(w))          # a stray scan line 9 degrees north of everything else
+    mask = np.zeros((h, w), bool)
+    mask[100:140, 200:260] = True                            # holes of ~120 x 200 km and ~40 x 60 km
+    mask[400:412, 50:70] = True
+    src = SwathDefinition(lon, lat)
+    proj = {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 10.0, "ellps": "WGS84"}
+    ext = (-1.6e6, -5.0e6, 1.6e6, -1.6e6)
+    dst = AreaDefinition("ps", "ps", "ps", proj, 360, 380, ext)
+    r = B200NearestResampler(src, dst)
+    r.precompute(mask=mask, radius_of_influence=radius)
+    assert r._current["method"] == "bucket"
+    vin, ref, got, _ = _check_indices(r, OSwath(lon, lat), OArea(proj, 360, 380, ext), radius, mask=mask)
+    stray = np.flatnonzero(vin.ravel())[got[got >= 0]] // w == 6
+    assert stray.sum() > 20                                  # the stray line was reached
+    assert (got < 0).sum() > 1000 and (got >= 0).sum() > 50000
+
+
 def test_swath_lonlats_may_be_device_tensors():
     """A swath whose lon/lat already live in HBM (what a device reader hands over) gives the result of the same
     swath passed as numpy arrays."""
