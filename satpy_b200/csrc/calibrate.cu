@@ -28,10 +28,33 @@ abi_calibrate_vec_kernel(const int16_t *__restrict__ counts, float *__restrict__
         int4 b = ld_stream_v4(src + 1);
         int w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         float r[16];
+#if !B200_BT_IEEE
+        if (c.mode == 2) {
+            // brightness temperature: the hardware-unit chain for all 16 pixels, then the rare unsafe ones again
+            unsigned slow_mask = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            r[2 * k] = b200_abi_cal_one((int)(short)(w[k] & 0xffff), c);
-            r[2 * k + 1] = b200_abi_cal_one((int)(short)((unsigned)w[k] >> 16), c);
+            for (int k = 0; k < 16; ++k) {
+                const int raw = (k & 1) ? (int)(short)((unsigned)w[k >> 1] >> 16) : (int)(short)(w[k >> 1] & 0xffff);
+                bool slow;
+                r[k] = b200_bt_fast(b200_abi_rad(raw, c), c, slow);
+                slow_mask |= (slow ? 1u : 0u) << k;
+            }
+            if (slow_mask) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (!((slow_mask >> k) & 1u)) continue;
+                    const int raw = (k & 1) ? (int)(short)((unsigned)w[k >> 1] >> 16) : (int)(short)(w[k >> 1] & 0xffff);
+                    r[k] = b200_bt_ieee(b200_abi_rad(raw, c), c);
+                }
+            }
+        } else
+#endif
+        {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                r[2 * k] = b200_abi_cal_one((int)(short)(w[k] & 0xffff), c);
+                r[2 * k + 1] = b200_abi_cal_one((int)(short)((unsigned)w[k] >> 16), c);
+            }
         }
         float *dst = out + 16 * i;
 #pragma unroll
