@@ -24,10 +24,29 @@ struct SunzDev {
     GeosFast fast;  // geostationary areas: table-driven inverse projection
     double gmst, ra, sin_dec, cos_dec;
     double limit_rad, limit_cos, max_rad, max_cos, span, li_lim;
-    int32_t has_max, lonlat_f32, method, pad;
+    int32_t has_max, lonlat_f32, method, alg;
+    // angle-free cos(sza) for geostationary areas (alg = 1): rotation by gmst - ra + lon_0 and the band of cos(sza)
+    // inside which the reference's rounded-angle flow is reproduced instead
+    double cos_a, sin_a, alg_lo, alg_hi;
 };
 
+// ALG: the caller only needs the CORRECTION (not cos(sza) itself) to 1e-5 relative.  Then, on geostationary areas with
+// float32 data, cos(sza) comes straight from the view vector: the ellipsoid normal is n = (vx, vy, vz / (1 - es)) and
+// cos(sza) = n . s / |n| with s the sun direction rotated into the satellite's meridian frame -- one rsqrt, no angles.
+// It differs from the reference's value (lon/lat rounded to float32, float32 deg2rad / sin / cos) by at most 4.7e-7
+// absolute, i.e. < 2.4e-6 relative in 1 / cos(sza) above alg_hi = 0.2; below alg_lo the result is masked / constant
+// whatever the last digits are.  In between (the 78.5 .. 95 degree band around the terminator, where the fall-off is
+// steep) the reference's flow is reproduced digit by digit as before.
+template <bool ALG>
 __device__ __forceinline__ double b200_cos_sza_pixel(const SunzDev &S, int64_t row, int64_t col) {
+    if (ALG && S.alg) {
+        double vx, vy, vz;
+        if (!geos_fast_vector(S.fast, row, col, vx, vy, vz)) return __longlong_as_double(0x7ff8000000000000LL);
+        const double u = S.fast.inv2 * vz;
+        const double num = fma(u, S.sin_dec, S.cos_dec * fma(S.cos_a, vx, -S.sin_a * vy));
+        const double cz = num * rsqrt(fma(u, u, fma(vx, vx, vy * vy)));
+        if (cz > S.alg_hi || cz < S.alg_lo) return cz;
+    }
     double lon, lat;
     bool ok = S.fast.enabled ? geos_fast_lonlat(S.fast, row, col, lon, lat) : b200_geo_lonlat(S.geo, row, col, lon, lat);
     if (!ok || !(lon < 1e30) || !(lat < 1e30)) return __longlong_as_double(0x7ff8000000000000LL);
@@ -93,7 +112,7 @@ cos_sza_kernel(double *__restrict__ out, const __grid_constant__ SunzDev S) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        out[i] = b200_cos_sza_pixel(S, S.geo.row0 + r, i - r * W);
+        out[i] = b200_cos_sza_pixel<false>(S, S.geo.row0 + r, i - r * W);
     }
 }
 
@@ -106,7 +125,7 @@ sunz_correct_kernel(const float *__restrict__ data, float *__restrict__ out, int
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        float corr = b200_sunz_corr(S, b200_cos_sza_pixel(S, S.geo.row0 + r, i - r * W));
+        float corr = b200_sunz_corr(S, b200_cos_sza_pixel<true>(S, S.geo.row0 + r, i - r * W));
         for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __fmul_rn(data[b * band_stride + i], corr);
     }
 }
@@ -120,7 +139,7 @@ sunz_correct_f64_kernel(const double *__restrict__ data, double *__restrict__ ou
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        double corr = b200_sunz_corr_d(S, b200_cos_sza_pixel(S, S.geo.row0 + r, i - r * W));
+        double corr = b200_sunz_corr_d(S, b200_cos_sza_pixel<false>(S, S.geo.row0 + r, i - r * W));
         for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __dmul_rn(data[b * band_stride + i], corr);
     }
 }
@@ -191,7 +210,7 @@ abi_vis_sunz_kernel(const __grid_constant__ FusedBands B, const __grid_constant_
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        float corr = b200_sunz_corr(S, b200_cos_sza_pixel(S, S.geo.row0 + r, i - r * W));
+        float corr = b200_sunz_corr(S, b200_cos_sza_pixel<true>(S, S.geo.row0 + r, i - r * W));
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             if (b < B.nbands) {
@@ -232,8 +251,20 @@ static int fill_sunz(SunzDev &S, const b200_geo_t *geo, const b200_sunz_t *sz, b
     S.lonlat_f32 = sz->lonlat_f32;
     S.method = sz->method;
     S.li_lim = 24.35 / (2.0 * S.limit_cos + sqrt(498.5225 * S.limit_cos * S.limit_cos + 1.0));
-    S.pad = 0;
+    S.alg = 0;  // set by sunz_enable_alg once the geostationary tables exist
+    S.cos_a = S.sin_a = S.alg_lo = S.alg_hi = 0.0;
     return B200_OK;
+}
+
+// angle-free cos(sza) where the correction tolerates it (see b200_cos_sza_pixel): geostationary area, float32 data
+static void sunz_enable_alg(SunzDev &S) {
+    if (!S.fast.enabled || !S.lonlat_f32) return;
+    const double a = S.gmst - S.ra + S.fast.lam0;
+    S.cos_a = cos(a);
+    S.sin_a = sin(a);
+    S.alg_hi = fmax(0.2, S.limit_cos + 1e-3);
+    S.alg_lo = (S.has_max ? fmin(S.max_cos, S.limit_cos) : S.limit_cos) - 1e-3;
+    S.alg = 1;
 }
 
 extern "C" int b200_cos_sza(const b200_geo_t *geo, const b200_sunz_t *sz, double *cos_sza, void *stream) {
@@ -263,6 +294,7 @@ extern "C" int b200_sunz_correct(const float *data, float *out, int32_t nbands, 
     B200_CHECK_ARG(nbands == 1 || band_stride >= n, "band stride smaller than one image");
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
+    sunz_enable_alg(S);
     sunz_correct_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands,
                                                                                   band_stride, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
@@ -341,6 +373,7 @@ extern "C" int b200_abi_vis_sunz(const int16_t *const *counts, float *const *out
     }
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
+    sunz_enable_alg(S);
     abi_vis_sunz_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
