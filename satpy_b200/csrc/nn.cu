@@ -64,6 +64,9 @@ __device__ __forceinline__ int b200_cell_of(const int32_t *__restrict__ band_off
 // ---------------------------------------------------------------------------------------- build
 // ONE pass over the source for both engines: validity, the record {x, y, z, raw index} by raw index (x = NaN marks an
 // invalid pixel) and, for the bucket engine, the cell of every valid point.
+// FAST: geostationary source (table-driven view vectors); a separate instantiation so that the register budget of the
+// general projection code does not lower the occupancy of the hot configuration.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restrict__ mask,
                         uint8_t *__restrict__ valid_input, double4 *__restrict__ rec, float4 *__restrict__ rec32,
@@ -76,7 +79,7 @@ nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restr
         int64_t r = i / W;
         double x = __longlong_as_double(0x7ff8000000000000LL), y = 0.0, z = 0.0, lam = 0.0, phi = 0.0;
         bool ok;
-        if (F.enabled) {
+        if (FAST) {
             // geostationary source: every pixel on the disk has a valid lon/lat; the point comes from the view
             // vector without trigonometric functions (the angles are only needed to pick a bucket cell)
             double sl, cl, sp, cp;
@@ -322,8 +325,12 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
     if (!bucket) NN_TRY(cudaMallocAsync((void **)&g->pts32, (size_t)n_src * sizeof(float4), s));
     rc = b200_geos_fast_prepare(src, &fast, s);
     if (rc) goto fail;
-    nn_source_points_kernel<<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(S, mask, valid_input, rec, g->pts32, cell_of,
-                                                                        g->band_off, phi0, inv_dphi, nbands, fast);
+    if (fast.enabled)
+        nn_source_points_kernel<true><<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(
+            S, mask, valid_input, rec, g->pts32, cell_of, g->band_off, phi0, inv_dphi, nbands, fast);
+    else
+        nn_source_points_kernel<false><<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(
+            S, mask, valid_input, rec, g->pts32, cell_of, g->band_off, phi0, inv_dphi, nbands, fast);
     NN_TRY(cudaGetLastError());
     b200_geos_fast_release(&fast, s);
     rc = nn_prefix(g, valid_input, s);

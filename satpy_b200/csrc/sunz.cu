@@ -37,9 +37,11 @@ struct SunzDev {
 // absolute, i.e. < 2.4e-6 relative in 1 / cos(sza) above alg_hi = 0.2; below alg_lo the result is masked / constant
 // whatever the last digits are.  In between (the 78.5 .. 95 degree band around the terminator, where the fall-off is
 // steep) the reference's flow is reproduced digit by digit as before.
-template <bool ALG>
+// FAST: geostationary area (table-driven inverse projection); separate instantiations keep the general projection code,
+// and its register budget, out of the hot configuration.
+template <bool ALG, bool FAST>
 __device__ __forceinline__ double b200_cos_sza_pixel(const SunzDev &S, int64_t row, int64_t col) {
-    if (ALG && S.alg) {
+    if (ALG && FAST && S.alg) {
         double vx, vy, vz;
         if (!geos_fast_vector(S.fast, row, col, vx, vy, vz)) return __longlong_as_double(0x7ff8000000000000LL);
         const double u = S.fast.inv2 * vz;
@@ -48,7 +50,7 @@ __device__ __forceinline__ double b200_cos_sza_pixel(const SunzDev &S, int64_t r
         if (cz > S.alg_hi || cz < S.alg_lo) return cz;
     }
     double lon, lat;
-    bool ok = S.fast.enabled ? geos_fast_lonlat(S.fast, row, col, lon, lat) : b200_geo_lonlat(S.geo, row, col, lon, lat);
+    bool ok = FAST ? geos_fast_lonlat(S.fast, row, col, lon, lat) : b200_geo_lonlat(S.geo, row, col, lon, lat);
     if (!ok || !(lon < 1e30) || !(lat < 1e30)) return __longlong_as_double(0x7ff8000000000000LL);
     double sl, cl, lon_r;
     if (S.lonlat_f32) {
@@ -105,6 +107,7 @@ __device__ __forceinline__ float b200_sunz_corr(const SunzDev &S, double cz) {
     return (float)(gf * S.li_lim);
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 cos_sza_kernel(double *__restrict__ out, const __grid_constant__ SunzDev S) {
     const int64_t W = S.geo.width;
@@ -112,11 +115,12 @@ cos_sza_kernel(double *__restrict__ out, const __grid_constant__ SunzDev S) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        out[i] = b200_cos_sza_pixel<false>(S, S.geo.row0 + r, i - r * W);
+        out[i] = b200_cos_sza_pixel<false, FAST>(S, S.geo.row0 + r, i - r * W);
     }
 }
 
 // One thread = one pixel, all bands (the factor is shared by every band of the area).
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 sunz_correct_kernel(const float *__restrict__ data, float *__restrict__ out, int nbands, int64_t band_stride,
                     const __grid_constant__ SunzDev S) {
@@ -125,12 +129,13 @@ sunz_correct_kernel(const float *__restrict__ data, float *__restrict__ out, int
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        float corr = b200_sunz_corr(S, b200_cos_sza_pixel<true>(S, S.geo.row0 + r, i - r * W));
+        float corr = b200_sunz_corr(S, b200_cos_sza_pixel<true, FAST>(S, S.geo.row0 + r, i - r * W));
         for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __fmul_rn(data[b * band_stride + i], corr);
     }
 }
 
 // float64 data: lon/lat are not rounded (S.lonlat_f32 = 0), the product is float64
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 sunz_correct_f64_kernel(const double *__restrict__ data, double *__restrict__ out, int nbands, int64_t band_stride,
                         const __grid_constant__ SunzDev S) {
@@ -139,7 +144,7 @@ sunz_correct_f64_kernel(const double *__restrict__ data, double *__restrict__ ou
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        double corr = b200_sunz_corr_d(S, b200_cos_sza_pixel<false>(S, S.geo.row0 + r, i - r * W));
+        double corr = b200_sunz_corr_d(S, b200_cos_sza_pixel<false, FAST>(S, S.geo.row0 + r, i - r * W));
         for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __dmul_rn(data[b * band_stride + i], corr);
     }
 }
@@ -203,6 +208,7 @@ struct FusedBands {
 };
 
 // Fused ABI reflective-band calibration + SunZenithCorrector: counts -> radiance -> % -> * corr.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 abi_vis_sunz_kernel(const __grid_constant__ FusedBands B, const __grid_constant__ SunzDev S) {
     const int64_t W = S.geo.width;
@@ -210,7 +216,7 @@ abi_vis_sunz_kernel(const __grid_constant__ FusedBands B, const __grid_constant_
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t r = i / W;
-        float corr = b200_sunz_corr(S, b200_cos_sza_pixel<true>(S, S.geo.row0 + r, i - r * W));
+        float corr = b200_sunz_corr(S, b200_cos_sza_pixel<true, FAST>(S, S.geo.row0 + r, i - r * W));
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             if (b < B.nbands) {
@@ -276,7 +282,8 @@ extern "C" int b200_cos_sza(const b200_geo_t *geo, const b200_sunz_t *sz, double
     B200_CHECK_ARG(cos_sza != nullptr, "NULL output");
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
-    cos_sza_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(cos_sza, S);
+    if (S.fast.enabled) cos_sza_kernel<true><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(cos_sza, S);
+    else cos_sza_kernel<false><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(cos_sza, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -295,8 +302,10 @@ extern "C" int b200_sunz_correct(const float *data, float *out, int32_t nbands, 
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
     sunz_enable_alg(S);
-    sunz_correct_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands,
-                                                                                  band_stride, S);
+    if (S.fast.enabled)
+        sunz_correct_kernel<true><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
+    else
+        sunz_correct_kernel<false><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -315,7 +324,10 @@ extern "C" int b200_sunz_correct_f64(const double *data, double *out, int32_t nb
     B200_CHECK_ARG(nbands == 1 || band_stride >= n, "band stride smaller than one image");
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
-    sunz_correct_f64_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
+    if (S.fast.enabled)
+        sunz_correct_f64_kernel<true><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
+    else
+        sunz_correct_f64_kernel<false><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -374,7 +386,8 @@ extern "C" int b200_abi_vis_sunz(const int16_t *const *counts, float *const *out
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
     sunz_enable_alg(S);
-    abi_vis_sunz_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
+    if (S.fast.enabled) abi_vis_sunz_kernel<true><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
+    else abi_vis_sunz_kernel<false><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
