@@ -41,6 +41,12 @@ __device__ __forceinline__ float b200_bt_fast(float rad, const b200_abi_cal_t &c
     return __fdividef(__fsub_rn(t, c.bc1), c.bc2);
 }
 
+// radiance (mode 0) or reflectance in % (mode 1) only
+__device__ __forceinline__ float b200_abi_cal_vis(int raw16, const b200_abi_cal_t &c) {
+    float rad = b200_abi_rad(raw16, c);
+    return c.mode == 0 ? rad : __fmul_rn(__fmul_rn(rad, c.refl_factor), 100.0f);
+}
+
 __device__ __forceinline__ float b200_abi_cal_one(int raw16, const b200_abi_cal_t &c) {
     float rad = b200_abi_rad(raw16, c);
     if (c.mode == 0) return rad;

@@ -17,7 +17,9 @@ struct AbiCalDev {
 };
 
 // 16 pixels per thread per iteration: two independent 128-bit loads in flight, four 128-bit stores.
-__global__ void __launch_bounds__(256)
+// BT: the brightness-temperature instantiation (75 registers); radiance / reflectance keep their 38.
+template <bool BT>
+__global__ void __launch_bounds__(256, BT ? 3 : 6)
 abi_calibrate_vec_kernel(const int16_t *__restrict__ counts, float *__restrict__ out, int64_t n_vec16,
                          const __grid_constant__ AbiCalDev P) {
     const b200_abi_cal_t &c = P.c;
@@ -29,7 +31,7 @@ abi_calibrate_vec_kernel(const int16_t *__restrict__ counts, float *__restrict__
         int w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         float r[16];
 #if !B200_BT_IEEE
-        if (c.mode == 2) {
+        if (BT) {
             // brightness temperature: the hardware-unit chain for all 16 pixels, then the rare unsafe ones again
             unsigned slow_mask = 0;
 #pragma unroll
@@ -52,8 +54,13 @@ abi_calibrate_vec_kernel(const int16_t *__restrict__ counts, float *__restrict__
         {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                r[2 * k] = b200_abi_cal_one((int)(short)(w[k] & 0xffff), c);
-                r[2 * k + 1] = b200_abi_cal_one((int)(short)((unsigned)w[k] >> 16), c);
+                if (BT) {  // only with B200_BT_IEEE
+                    r[2 * k] = b200_abi_cal_one((int)(short)(w[k] & 0xffff), c);
+                    r[2 * k + 1] = b200_abi_cal_one((int)(short)((unsigned)w[k] >> 16), c);
+                } else {
+                    r[2 * k] = b200_abi_cal_vis((int)(short)(w[k] & 0xffff), c);
+                    r[2 * k + 1] = b200_abi_cal_vis((int)(short)((unsigned)w[k] >> 16), c);
+                }
             }
         }
         float *dst = out + 16 * i;
@@ -84,7 +91,8 @@ extern "C" int b200_abi_calibrate(const int16_t *counts, float *out, int64_t n, 
     int64_t n_vec = aligned ? n / 16 : 0;
     if (n_vec > 0) {
         int grid = b200_grid_for(n_vec, 256, 8);
-        abi_calibrate_vec_kernel<<<grid, 256, 0, s>>>(counts, out, n_vec, P);
+        if (cal->mode == 2) abi_calibrate_vec_kernel<true><<<grid, 256, 0, s>>>(counts, out, n_vec, P);
+        else abi_calibrate_vec_kernel<false><<<grid, 256, 0, s>>>(counts, out, n_vec, P);
         B200_LAUNCH_CHECK();
     }
     int64_t done = n_vec * 16;

@@ -220,7 +220,7 @@ abi_vis_sunz_kernel(const __grid_constant__ FusedBands B, const __grid_constant_
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             if (b < B.nbands) {
-                float refl = b200_abi_cal_one((int)B.counts[b][i], B.cal[b]);
+                float refl = b200_abi_cal_vis((int)B.counts[b][i], B.cal[b]);  // mode 1 (checked by the entry point)
                 st_stream_f1(B.out[b] + i, __fmul_rn(refl, corr));
             }
         }
