@@ -89,6 +89,10 @@ int b200_area_lonlats(const b200_geo_t *geo /* host */, double *lons, double *la
 /* --------------------------------------------------------------- calibration
  * ABI L1b: readers/core/abi.py:138-174 (_adjust_data) + readers/abi_l1b.py:133-173.
  * mode 0 radiance, 1 reflectance [%], 2 brightness temperature [K].
+ * Radiance and reflectance are bit-identical to numpy's float32 arithmetic; the Planck inversion of
+ * mode 2 uses the hardware reciprocal / log2 units (within 4e-7 relative of the correctly rounded
+ * chain; numpy's own float32 log is not correctly rounded either) and redoes pixels whose
+ * logarithm argument is below 2 with IEEE divisions and logf.
  */
 typedef struct b200_abi_cal {
     int32_t mode;
@@ -165,7 +169,11 @@ typedef struct b200_sunz {
 int b200_cos_sza(const b200_geo_t *geo, const b200_sunz_t *sz, double *cos_sza, void *stream);
 
 /* out = data * corr(cos_sza(lon,lat)); lon/lat derived in-kernel from geo.
- * nbands images of geo->nrows*width pixels, band stride = band_stride elements. */
+ * nbands images of geo->nrows*width pixels, band stride = band_stride elements.
+ * On geostationary areas cos(sza) comes straight from the view vector (no angles) where the
+ * correction is insensitive to its last digits (cos(sza) > 0.2 or beyond max_sza: within 2.4e-6
+ * relative of the reference); the band around the terminator reproduces the reference's float32
+ * rounding of lon/lat digit by digit, as b200_cos_sza always does. */
 int b200_sunz_correct(const float *data, float *out, int32_t nbands, int64_t band_stride,
                       const b200_geo_t *geo, const b200_sunz_t *sz, void *stream);
 
@@ -210,7 +218,9 @@ int b200_abi_vis_sunz(const int16_t *const *counts /* host array of device ptrs 
  */
 typedef struct b200_nn_grid b200_nn_grid_t; /* opaque, owned by the library */
 
-/* Build the bucket grid over the valid source points.
+/* Build the search structure over the valid source points (bucket grid: cells of a few points
+ * each, sized from a sample of the source, independent of `radius`; fixed grid: the source
+ * lattice itself).
  *   src            source geometry; the grid covers its row window [row0, row0+nrows) (the
  *                  whole grid normally; a band of rows when the target is row-tiled across GPUs,
  *                  cf. Scene._reduce_data, scene.py:930-954).  Source pixel indices and the
