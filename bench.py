@@ -7,10 +7,12 @@ Workload (BASELINE.json configs[4], the configuration the metric is quoted on; i
 synthetic ABI C02 10848 x 10848 int16 counts on ``goes_east_abi_f_1km`` -> reflectance [%] ->
 SunZenithCorrector -> nearest-neighbour to the 0.5 km global equirectangular grid 80150 x 40075
 (3212 Mpix, 12.85 GB float32), radius_of_influence 2000 m.  One "step" is one full pass:
-fused calibrate+sunz kernel, search-structure build, fused query+gather, (N > 1) one NCCL all-gather.
-With N GPUs the target rows are cut into N x subtiles blocks handed out round-robin, each block fed only
-the source rows that can reach it, and every group of N blocks is all-gathered in place while the next
-group is searched (strong scaling: the total work is fixed).
+fused calibrate+sunz kernel, search-structure build, fused query+gather, (N > 1) assembly of the image on
+every rank.  With N GPUs the target rows are cut into N x subtiles blocks handed out round-robin, each block
+fed only the source rows that can reach it; a finished block is pushed into every peer's copy of the image by
+the copy engines over NVLink (symmetric memory, ``--exchange p2p``) -- or every group of N blocks is
+all-gathered in place by NCCL (``--exchange nccl``) -- while the next block is searched (strong scaling: the
+total work is fixed).  The all-gather result is verified after the timed region (``exchange.verified``).
 
 One JSON line is printed by rank 0 (see the keys in ``main``).  ``value`` is whole-job output Mpix/s
 with inputs resident in HBM; ``e2e`` is the same through the public host-buffer API with the
@@ -50,8 +52,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--subtiles", type=int, default=0,
-                    help="N > 1: row blocks per rank, each group of N blocks all-gathered while the next is searched; "
-                         "0 = automatic: max(1, 8 // N), the measured optimum at N = 2, 4 and 8")
+                    help="N > 1: row blocks per rank, each exchanged while the next is searched; 0 = automatic "
+                         "(see effective_subtiles)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: how the image is assembled on every rank: p2p = copy-engine pushes into the peers' "
+                         "symmetric images (satpy_b200.parallel.PeerImage), nccl = in-place NCCL all-gathers; "
+                         "auto = p2p, nccl if symmetric memory cannot be set up")
     return ap.parse_args()
 
 
@@ -184,23 +190,31 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def effective_subtiles(args):
+def effective_subtiles(args, exchange=None):
     if args.gpus <= 1:
         return 1
-    # automatic: keep every rank's contribution to one all-gather near total / 8 (1.6 GB for config 5).  Measured on
-    # 8 x B200 (ms per step): N=2 S=1 31.0, S=4 22.5 | N=4 S=1 33.2, S=2 20.5, S=4 30.4 | N=8 S=1 21.6, S=2 31.5, S=4 30.5
-    return args.subtiles if args.subtiles > 0 else max(1, 8 // args.gpus)
+    if args.subtiles > 0:
+        return args.subtiles
+    if (exchange or args.exchange) == "nccl":
+        # keep every rank's contribution to one all-gather near total / 8 (1.6 GB for config 5).  Measured on
+        # 8 x B200 (ms per step): N=2 S=1 31.0, S=4 22.5 | N=4 S=1 33.2, S=2 20.5, S=4 30.4 | N=8 S=1 21.6, S=2 31.5, S=4 30.5
+        return max(1, 8 // args.gpus)
+    # copy-engine pushes cost the same in small pieces; 4 blocks per rank leave little to send after the last search
+    # without multiplying launches and round barriers.  Measured (ms per step): N=2 S=4 17.5, S=8 18.2 | N=4 S=4 18.5,
+    # S=8 18.9, S=2 24.8 (before the rounds ran in lock step)
+    return 4
 
 
-def config_dict(sp, dp, radius, args):
-    nsub = effective_subtiles(args)
+def config_dict(sp, dp, radius, args, exchange=None):
+    nsub = effective_subtiles(args, exchange)
+    how = (f"{nsub} in-place all-gathers" if exchange == "nccl" else
+           "each block pushed into the peers' symmetric images by the copy engines")
     return {"workload": f"configs[4]: synthetic ABI {BAND} {sp[1]}x{sp[2]} full-disk ({SRC_AREA}) calibrate+sunz+nearest "
                         f"-> {dp[1]}x{dp[2]} {DST_AREA}, radius_of_influence {radius:g} m, row tiles over {args.gpus} GPU(s)",
             "source_shape": [sp[2], sp[1]], "target_shape": [dp[2], dp[1]], "radius_m": radius, "seed": SEED,
             "l2": "inputs and outputs larger than L2 (no flush needed)" if args.scale >= 0.5 else "debug scale",
-            "scale": args.scale, "parallelism": (f"{args.gpus * nsub} row blocks round-robin over {args.gpus} GPUs, {nsub} in-place "
-                             f"all-gathers overlapped with the search"
-                            if args.gpus > 1 else "single GPU")}
+            "scale": args.scale, "parallelism": (f"{args.gpus * nsub} row blocks round-robin over {args.gpus} GPUs, {how}, "
+                             f"overlapped with the search" if args.gpus > 1 else "single GPU")}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -235,9 +249,27 @@ def run_b200(args):
     # so that every rank gets blocks from all latitudes (on-disk and off-disk rows cost very differently) and the N
     # blocks of group k are contiguous in the image: one in-place all-gather per group, overlapping the next group's
     # search.  Each block is fed only the band of source rows that can reach it.
-    nsub = effective_subtiles(args) if world > 1 else 1
+    exchange, peer_image = None, None
+    if world > 1:
+        exchange = "nccl" if args.exchange == "nccl" else "p2p"
+        ok = torch.ones(1, device="cuda")
+        if exchange == "p2p":
+            try:
+                nsub = effective_subtiles(args, "p2p")
+                block_rows, _ = parallel.row_tiles(dst.height, world * nsub)
+                peer_image = parallel.PeerImage((world * nsub * block_rows, dst.width), torch.float32)
+            except Exception as exc:  # noqa: BLE001 -- any failure to set up peer mappings means "use NCCL"
+                print(f"rank {rank}: symmetric memory unavailable ({type(exc).__name__}: {exc})", file=sys.stderr)
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if exchange == "p2p" and float(ok.item()) == 0.0:
+            if args.exchange == "p2p":
+                raise SystemExit("--exchange p2p: symmetric memory could not be set up on every rank")
+            exchange, peer_image = "nccl", None
+    nsub = effective_subtiles(args, exchange) if world > 1 else 1
     block_rows, blocks_all = parallel.row_tiles(dst.height, world * nsub)
-    full = torch.empty((world * nsub * block_rows, dst.width), dtype=torch.float32, device="cuda")
+    full = (peer_image.local if peer_image is not None else
+            torch.empty((world * nsub * block_rows, dst.width), dtype=torch.float32, device="cuda"))
     blocks = []
     for k in range(nsub):
         b = k * world + rank
@@ -247,18 +279,20 @@ def run_b200(args):
         pipe = ABIResamplePipeline(src, dst, radius, row_window=(row0, nrows), src_row_window=(s_row0, s_nrows))
         cwin = np.ascontiguousarray(counts[s_row0:s_row0 + s_nrows])
         cpin = torch.from_numpy(cwin).pin_memory() if s_nrows else torch.empty((0, src.width), dtype=torch.int16)
-        blocks.append({"pipe": pipe, "counts_pin": cpin, "counts_dev": cpin.cuda(),
+        blocks.append({"pipe": pipe, "counts_pin": cpin, "counts_dev": cpin.cuda(), "row0": b * block_rows, "nrows": nrows,
                        "out": full[b * block_rows: b * block_rows + nrows],
                        "slot": full[b * block_rows: (b + 1) * block_rows],
                        "group": full[k * world * block_rows: (k + 1) * world * block_rows]})
-    comm_stream = torch.cuda.Stream(priority=-1) if world > 1 else None   # the exchange gets SMs first
+    comm_stream = torch.cuda.Stream(priority=-1) if exchange == "nccl" else None   # the exchange gets SMs first
 
     def step():
         main = torch.cuda.current_stream()
         works = []
         for blk in blocks:
             blk["pipe"].run(blk["counts_dev"], cal, demo.START_TIME, out=blk["out"])
-            if world > 1:
+            if exchange == "p2p":
+                peer_image.push_rows(blk["row0"], blk["nrows"])
+            elif exchange == "nccl":
                 ev = torch.cuda.Event()
                 ev.record(main)
                 with torch.cuda.stream(comm_stream):
@@ -266,8 +300,10 @@ def run_b200(args):
                     works.append(dist.all_gather_into_tensor(blk["group"], blk["slot"], async_op=True))
         for w in works:
             w.wait()
-        if world > 1:
+        if exchange == "nccl":
             main.wait_stream(comm_stream)
+        elif exchange == "p2p":
+            peer_image.finish()
 
     def barrier():
         torch.cuda.synchronize()
@@ -302,6 +338,35 @@ def run_b200(args):
     clocks = sampler.stop() if sampler else None
     n_out_total = dst.width * dst.height
     value = n_out_total / 1e6 / (ms_step / 1e3)
+
+    if peer_image is not None and os.environ.get("B200_TRACE_EXCHANGE") and rank == 0:
+        # diagnostics: when each copy of one step started / ended relative to the step's first kernel
+        t0 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer_image.trace = []
+        t0.record()
+        step()
+        torch.cuda.synchronize()
+        for peer, row0, nbytes, e0, e1 in peer_image.trace:
+            print(f"push to {peer} rows {row0}: start {t0.elapsed_time(e0):7.2f} ms, {e0.elapsed_time(e1):6.2f} ms, "
+                  f"{nbytes / e0.elapsed_time(e1) / 1e6:6.0f} GB/s", file=sys.stderr)
+        peer_image.trace = None
+    elif peer_image is not None and os.environ.get("B200_TRACE_EXCHANGE"):
+        torch.cuda.synchronize()
+        dist.barrier()
+        step()
+        torch.cuda.synchronize()
+
+    # ---- the exchange delivered every block to every rank: checksums of the blocks agree across ranks
+    exchange_info = None
+    if world > 1:
+        sums = torch.stack([full[b * block_rows: b * block_rows + blocks_all[b][1]].view(torch.int32).sum(dtype=torch.int64)
+                            for b in range(world * nsub)])
+        seen = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(seen, sums)
+        exchange_info = {"kind": exchange, "blocks": world * nsub,
+                         "verified": bool(all(torch.equal(v, sums) for v in seen)) and bool((sums != 0).any())}
 
     # ---- per-stage device times on this rank (CUDA events on the launching stream)
     stages = {}
@@ -397,8 +462,10 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 values / f64 geometry", "data": "synthetic",
-            "config": config_dict(sp, dp, radius, args), "clocks": clocks, "gpu_launches": launches,
+            "config": config_dict(sp, dp, radius, args, exchange), "clocks": clocks, "gpu_launches": launches,
             "roofline": roofline, "stages": stages, "e2e": e2e}
+    if exchange_info is not None:
+        line["exchange"] = exchange_info
 
     if world == 1 and not args.no_cpu_baseline:
         sample = CpuSample(counts, sp, dp, radius)

@@ -206,6 +206,25 @@ dist.destroy_process_group()
 '''
 
 
+def test_peer_exchange_rounds_are_collision_free():
+    """PeerImage's schedule: in every round the destinations form a permutation without fixed points, and over the
+    world_size - 1 rounds every rank reaches every peer exactly once."""
+    from satpy_b200.parallel import round_peer
+    for world in (2, 3, 4, 8):
+        reached = {r: set() for r in range(world)}
+        for k in range(1, world):
+            dests = [round_peer(r, k, world) for r in range(world)]
+            assert sorted(dests) == list(range(world))
+            assert all(d != r for r, d in enumerate(dests))
+            for r, d in enumerate(dests):
+                reached[r].add(d)
+        assert all(reached[r] == set(range(world)) - {r} for r in range(world))
+    with pytest.raises(ValueError):
+        round_peer(0, 0, 4)
+    with pytest.raises(ValueError):
+        round_peer(0, 4, 4)
+
+
 def test_all_gather_rows_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
