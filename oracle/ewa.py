@@ -189,3 +189,11 @@ def fornav(cols, rows, dst_shape, data, rows_per_scan=0, fill=np.nan, weight_cou
     if return_grids:
         return counts, out, grid_w.reshape(-1, gh, gw), grid_a.reshape(-1, gh, gw)
     return counts, out
+
+
+def fornav_accumulate(cols, rows, dst_shape, data, **kwargs):
+    """The two accumulation grids (sum of weights, sum of weight * value) of ``fornav`` before normalisation, for
+    2-D ``data``: what one input chunk contributes in pyresample's dask wrapper, which SUMS these pairs over the input
+    chunks and normalises once.  Test infrastructure like the rest of this module."""
+    _, _, grid_w, grid_a = fornav(cols, rows, dst_shape, data, return_grids=True, **kwargs)
+    return grid_w[0], grid_a[0]

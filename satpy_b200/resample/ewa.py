@@ -34,6 +34,33 @@ def ewa_params(weight_count=10000, weight_min=0.01, weight_distance_max=1.0, wei
     return p
 
 
+def scan_band(height: int, rows_per_scan: int, scan_rows=None):
+    """Validate a band of swath rows ``(row0, nrows)`` for fornav: it has to start on a scan boundary and hold whole
+    scans (ellipse parameters are computed per scan).  ``None``: the whole swath."""
+    if scan_rows is None:
+        return 0, height
+    row0, nrows = int(scan_rows[0]), int(scan_rows[1])
+    if row0 < 0 or nrows < 0 or row0 + nrows > height:
+        raise ValueError(f"scan_rows {scan_rows} outside the {height}-row swath")
+    rps = rows_per_scan if rows_per_scan > 0 else height
+    if row0 % rps or nrows % rps:
+        raise ValueError(f"scan_rows {scan_rows} does not hold whole scans of {rps} rows")
+    return row0, nrows
+
+
+def scan_bands(height: int, rows_per_scan: int, world_size: int):
+    """Split a swath of ``height`` rows into ``world_size`` bands of whole scans, as even as possible (the last ranks
+    may get an empty band)."""
+    rps = rows_per_scan if rows_per_scan > 0 else height
+    nscans = height // rps
+    per = -(-nscans // world_size)
+    bands = []
+    for r in range(world_size):
+        s0 = min(nscans, r * per)
+        bands.append((s0 * rps, (min(nscans, s0 + per) - s0) * rps))
+    return bands
+
+
 class B200EWAResampler:
     """ll2cr + fornav; the accumulation grids live on the device for the duration of ``compute``."""
 
@@ -65,7 +92,11 @@ class B200EWAResampler:
 
     def compute(self, data, cache_id=None, rows_per_scan=None, fill_value=None, weight_count=10000, weight_min=0.01,
                 weight_distance_max=1.0, weight_delta_max=10.0, weight_sum_min=-1.0, maximum_weight_mode=False,
-                **kwargs):
+                scan_rows=None, group=None, **kwargs):
+        """``fornav``.  ``scan_rows=(row0, nrows)`` restricts the accumulation to a band of whole scans of the swath
+        (``data`` is still the full swath) and ``group`` names a ``torch.distributed`` process group whose ranks each
+        accumulate their own band: the (sum of weights, sum of weighted values) grids are summed over the ranks before
+        the normalisation, the decomposition pyresample's dask wrapper uses over input chunks."""
         del kwargs, cache_id
         torch = _lib.require_cuda()
         lib = _lib.load()
@@ -84,6 +115,9 @@ class B200EWAResampler:
         src, dst = self.source_geo_def, self.target_geo_def
         if tuple(t.shape[-2:]) != src.shape:
             raise ValueError(f"data shape {tuple(t.shape)} does not end with the source shape {src.shape}")
+        row0, nrows = scan_band(src.height, int(rows_per_scan), scan_rows)
+        if group is not None and maximum_weight_mode:
+            raise NotImplementedError("maximum_weight_mode over several ranks needs a max-by-weight reduction")
         lead = tuple(t.shape[:-2])
         nbands = int(np.prod(lead)) if lead else 1
         out = torch.empty(lead + dst.shape, dtype=torch.float32, device="cuda")
@@ -95,10 +129,18 @@ class B200EWAResampler:
             p = ewa_params(weight_count, weight_min, weight_distance_max, weight_delta_max, weight_sum_min,
                            maximum_weight_mode)
             stream = _lib.stream_ptr(torch)
-            _lib.check(lib.b200_fornav_accum(self._cr["cols"].data_ptr(), self._cr["rows"].data_ptr(),
-                                             1 if self._cr["f32"] else 0, src.height, src.width, int(rows_per_scan),
-                                             t.data_ptr(), nbands, src.size, float("nan"), dst.height, dst.width,
-                                             weights.data_ptr(), accums.data_ptr(), C.byref(p), stream))
+            if nrows > 0:
+                cr_item = 4 if self._cr["f32"] else 8
+                first = row0 * src.width
+                _lib.check(lib.b200_fornav_accum(self._cr["cols"].data_ptr() + first * cr_item,
+                                                 self._cr["rows"].data_ptr() + first * cr_item,
+                                                 1 if self._cr["f32"] else 0, nrows, src.width, int(rows_per_scan),
+                                                 t.data_ptr() + first * 4, nbands, src.size, float("nan"), dst.height,
+                                                 dst.width, weights.data_ptr(), accums.data_ptr(), C.byref(p), stream))
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(weights, op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(accums, op=dist.ReduceOp.SUM, group=group)
             counts = (C.c_int64 * nbands)()
             _lib.check(lib.b200_fornav_finalize(weights.data_ptr(), accums.data_ptr(), out.data_ptr(), nbands, dst.size,
                                                 C.byref(p), float(fill_value), counts, stream))

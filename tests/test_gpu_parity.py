@@ -671,6 +671,36 @@ def test_fornav_matches_oracle(rows_per_scan, bowtie, maxmode):
         assert abs(int(r.valid_counts[0]) - int(cnt[0])) <= max(3, 2e-4 * dst.size)
 
 
+def test_fornav_scan_band_equals_the_oracle_on_that_band():
+    """``scan_rows`` (what each rank of a multi-GPU EWA accumulates before the grids are summed): the
+    result of a band of whole scans is the oracle's result for that band alone, and the bands of a split add up."""
+    import torch
+    from oracle import ewa as oewa
+    from satpy_b200.resample import B200EWAResampler
+    from satpy_b200.resample.ewa import scan_bands
+    lon, lat, rps = demo.viirs_like_swath(bowtie=0.3)
+    dst, _ = _ps_target()
+    rng = np.random.default_rng(14)
+    data = rng.uniform(0, 120, size=lon.shape).astype(np.float32)
+    r = B200EWAResampler(SwathDefinition(lon, lat), dst)
+    r.precompute()
+    cols, rows = r._cr["cols"].cpu().numpy(), r._cr["rows"].cpu().numpy()
+    bands = scan_bands(lon.shape[0], rps, 3)
+    assert sum(n for _, n in bands) == lon.shape[0]
+    row0, nrows = bands[1]
+    out = r.compute(data, rows_per_scan=rps, scan_rows=(row0, nrows))
+    sl = slice(row0, row0 + nrows)
+    _, exp = oewa.fornav(cols[sl], rows[sl], dst.shape, data[sl], rows_per_scan=rps)
+    assert (np.isnan(out) != np.isnan(exp)).mean() < 2e-4
+    ok = ~np.isnan(out) & ~np.isnan(exp)
+    assert ok.mean() > 0.05
+    np.testing.assert_allclose(out[ok], exp[ok], rtol=1e-4)
+    with pytest.raises(ValueError):
+        r.compute(data, rows_per_scan=rps, scan_rows=(row0 + 1, nrows))
+    with pytest.raises(ValueError):
+        r.compute(data, rows_per_scan=rps, scan_rows=(row0, lon.shape[0]))
+
+
 def test_fornav_properties():
     """Size-independent properties: a constant field is reproduced, NaN input is skipped, an empty overlap is all fill."""
     from satpy_b200.resample import B200EWAResampler

@@ -206,6 +206,65 @@ dist.destroy_process_group()
 '''
 
 
+def test_ewa_scan_bands():
+    from satpy_b200.resample.ewa import scan_band, scan_bands
+    assert scan_bands(7680, 16, 8) == [(i * 960, 960) for i in range(8)]
+    bands = scan_bands(16 * 10, 16, 4)
+    assert bands == [(0, 48), (48, 48), (96, 48), (144, 16)] and sum(n for _, n in bands) == 160
+    assert scan_bands(32, 16, 4) == [(0, 16), (16, 16), (32, 0), (32, 0)]
+    assert scan_bands(100, 0, 2) == [(0, 100), (100, 0)]          # rows_per_scan = 0: the swath is one scan
+    assert scan_band(160, 16, None) == (0, 160)
+    assert scan_band(160, 16, (32, 64)) == (32, 64)
+    for bad in ((8, 16), (16, 24), (-16, 16), (144, 32)):
+        with pytest.raises(ValueError):
+            scan_band(160, 16, bad)
+    with pytest.raises(ValueError):
+        scan_band(160, 0, (0, 80))
+
+
+_EWA_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from oracle import ewa as oewa
+from oracle.projections import Area
+from satpy_b200 import demo
+from satpy_b200.resample.ewa import scan_bands
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lon, lat, rps = demo.viirs_like_swath(nscans=6, ncols=120)
+proj = {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 0.0, "ellps": "WGS84"}
+dst = Area(proj, 60, 60, (-1.2e6, -2.4e6, 0.3e6, -0.9e6))
+_, cols, rows = oewa.ll2cr(lon, lat, dst)
+data = np.random.default_rng(2).uniform(0, 100, lon.shape).astype(np.float32)
+row0, nrows = scan_bands(lon.shape[0], rps, world)[rank]
+sl = slice(row0, row0 + nrows)
+w, a = oewa.fornav_accumulate(cols[sl], rows[sl], (60, 60), data[sl], rows_per_scan=rps)
+tw, ta = torch.from_numpy(w.astype(np.float64)), torch.from_numpy(a.astype(np.float64))
+dist.all_reduce(tw); dist.all_reduce(ta)
+w_all, a_all = oewa.fornav_accumulate(cols, rows, (60, 60), data, rows_per_scan=rps)
+np.testing.assert_allclose(tw.numpy(), w_all, rtol=1e-5, atol=1e-6)
+np.testing.assert_allclose(ta.numpy(), a_all, rtol=1e-5, atol=1e-4)
+dist.barrier()
+if rank == 0:
+    print("EWA_GLOO_OK", int((w_all > 0).sum()))
+dist.destroy_process_group()
+'''
+
+
+def test_ewa_scan_bands_sum_to_the_whole_world_size_2_gloo(tmp_path):
+    """Multi-GPU EWA (SURVEY.md 8e): ranks accumulate bands of whole scans and SUM their grids; checked with the
+    oracle's accumulation on two gloo ranks."""
+    script = tmp_path / "worker.py"
+    script.write_text(_EWA_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29633", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "EWA_GLOO_OK" in out.stdout
+
+
 def test_peer_exchange_rounds_are_collision_free():
     """PeerImage's schedule: in every round the destinations form a permutation without fixed points, and over the
     world_size - 1 rounds every rank reaches every peer exactly once."""
