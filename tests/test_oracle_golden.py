@@ -295,3 +295,84 @@ def test_observer_look_sanity():
     assert abs(el[4]) < 0.5                            # 81.3 degrees of longitude away: on the horizon
     alt, azs = osolar.get_alt_az(dt.datetime(2022, 1, 5, 12, 50, 0), np.array([-80., 40, 0, 40, 80]), np.array([-80., 40, 0, 40, 80]))
     assert (np.rad2deg(azs) % 360 > 0).all()           # test_angles.py:385-398
+
+
+# ------------------------------------------------- bilinear / EWA: known answers on regular geometry
+# The reference has no golden vector for these two rows (its tests mock pyresample), so the restatements are anchored
+# on cases whose answer follows from the published algorithm without running it: on a source grid that is regular in
+# the TARGET projection the quadrant corners are the enclosing cell and (t, s) are the textbook bilinear weights; a
+# swath that maps one-to-one onto grid cells makes fornav a fixed 3 x 3 weighted average.
+def test_bilinear_oracle_equals_regular_grid_interpolation():
+    from scipy.interpolate import RegularGridInterpolator
+
+    from oracle import bilinear as obil
+    proj = {"proj": "eqc", "lon_0": 10.0, "ellps": "WGS84"}
+    src = Area(proj, 50, 40, (-500e3, 200e3, 500e3, 1000e3))              # 20 km pixels
+    dst = Area(proj, 120, 90, (-301.23e3, 349.87e3, 298.77e3, 799.87e3))   # 5 km pixels, well inside, off the lattice
+    rng = np.random.default_rng(8)
+    data = rng.uniform(-5, 5, size=src.shape)
+    t, s, vin, idx = obil.get_bil_info(src, dst, radius_of_influence=50e3, neighbours=32)
+    assert vin.all() and idx.shape == (dst.width * dst.height, 4)
+    assert np.isfinite(t).all() and np.isfinite(s).all()
+    out = obil.get_sample_from_bil_info(data, t, s, vin, idx, dst.shape)
+    sx, sy = src.proj_vectors()
+    dx, dy = dst.proj_vectors()
+    interp = RegularGridInterpolator((sy[::-1], sx), data[::-1], method="linear")
+    gy, gx = np.meshgrid(dy, dx, indexing="ij")
+    expected = interp(np.stack([gy.ravel(), gx.ravel()], axis=1)).reshape(dst.shape)
+    np.testing.assert_allclose(out, expected, rtol=0, atol=1e-9)
+    # the four corners are the enclosing source cell: upper-left is one row up and one column left of lower-right
+    ul, ur, ll, lr = (idx[:, k] for k in range(4))
+    assert np.array_equal(ur - ul, np.ones_like(ul)) and np.array_equal(lr - ll, np.ones_like(ll))
+    assert np.array_equal(ll - ul, np.full_like(ul, src.width))
+
+
+def test_fornav_oracle_on_a_one_to_one_swath_is_a_fixed_weighted_average():
+    from scipy.ndimage import correlate
+
+    from oracle import ewa as oewa
+    h, w = 24, 30
+    rows, cols = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    rng = np.random.default_rng(9)
+    data = rng.uniform(1, 9, size=(h, w)).astype(np.float32)
+    # weight_distance_max = 1: only the pixel's own cell lies strictly inside its (circular) footprint
+    cnt, out = oewa.fornav(cols, rows, (h, w), data, rows_per_scan=4, weight_distance_max=1.0)
+    np.testing.assert_array_equal(out, data)
+    assert int(cnt[0]) == h * w
+    # weight_distance_max = 2: footprint radius 2 cells -> the 3 x 3 neighbourhood (q = 0, 1, 2 < qmax = 4), weights from
+    # the table wtab[int(q * count / qmax)] = exp(-alpha * qmax * int(...) / (count - 1)), alpha = -ln(weight_min) / qmax
+    count, wmin, dmax = 10000, 0.01, 2.0
+    qmax = dmax * dmax
+    alpha = -math.log(wmin) / qmax
+    wq = [math.exp(-alpha * qmax * int(q * count / qmax) / (count - 1)) for q in (0.0, 1.0, 2.0)]
+    kernel = np.array([[wq[2], wq[1], wq[2]], [wq[1], wq[0], wq[1]], [wq[2], wq[1], wq[2]]])
+    num = correlate(data.astype(np.float64), kernel, mode="constant", cval=0.0)
+    den = correlate(np.ones((h, w)), kernel, mode="constant", cval=0.0)
+    _, out2 = oewa.fornav(cols, rows, (h, w), data, rows_per_scan=4, weight_count=count, weight_min=wmin,
+                          weight_distance_max=dmax)
+    np.testing.assert_allclose(out2, num / den, rtol=2e-6)
+    # NaN samples are skipped, their cells are still filled from the neighbours
+    holes = data.copy()
+    holes[5, 7] = np.nan
+    _, out3 = oewa.fornav(cols, rows, (h, w), holes, rows_per_scan=4, weight_distance_max=dmax)
+    m = np.ones((h, w))
+    m[5, 7] = 0.0
+    num3 = correlate(np.where(m > 0, data, 0.0).astype(np.float64), kernel, mode="constant", cval=0.0)
+    den3 = correlate(m, kernel, mode="constant", cval=0.0)
+    np.testing.assert_allclose(out3, num3 / den3, rtol=2e-6)
+
+
+def test_ll2cr_oracle_is_the_affine_map_of_the_target_area():
+    from oracle import ewa as oewa
+    proj = {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 0.0, "ellps": "WGS84"}
+    dst = Area(proj, 40, 30, (-1.0e6, -3.0e6, 1.0e6, -1.5e6))
+    lon, lat = dst.get_lonlats()
+    n_in, cols, rows = oewa.ll2cr(lon, lat, dst)      # the area's own pixel centres land on integer (col, row)
+    assert n_in == dst.width * dst.height
+    jj, ii = np.meshgrid(np.arange(dst.width), np.arange(dst.height))
+    np.testing.assert_allclose(cols, jj, atol=1e-6)
+    np.testing.assert_allclose(rows, ii, atol=1e-6)
+    lon2 = lon.copy()
+    lon2[0, 0] = np.nan
+    n2, c2, r2 = oewa.ll2cr(lon2, lat, dst)
+    assert n2 == n_in - 1 and np.isnan(c2[0, 0]) and np.isnan(r2[0, 0])
