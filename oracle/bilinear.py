@@ -18,6 +18,8 @@ judge should read every parity claim against it as "partial".  Steps:
 4. fractional distances: general quadrilateral (quadratic in t), then "uprights parallel" where t is invalid, then
    parallelogram where still invalid; roots outside [0, 1] are NaN.
 5. ``p1 (1-s)(1-t) + p2 s (1-t) + p3 (1-s) t + p4 s t``; NaN -> ``fill_value``.
+
+Known-answer anchors (no reference vector exists): tests/test_oracle_golden.py::test_bilinear_oracle_equals_regular_grid_interpolation.
 """
 from __future__ import annotations
 

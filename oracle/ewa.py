@@ -10,6 +10,8 @@ incremental evaluation of ``q`` (``q += dq; dq += ddq``) so that the weight-tabl
 
 ``DaskEWAResampler`` runs the same ``fornav`` for every (input scan chunk, output chunk) pair and sums the weight and
 accumulation grids before normalising; that sum equals one full-grid pass, which is what is restated here.
+
+Known-answer anchors (no reference vector exists): tests/test_oracle_golden.py::test_fornav_oracle_on_a_one_to_one_swath_is_a_fixed_weighted_average / test_ll2cr_oracle_is_the_affine_map_of_the_target_area.
 """
 from __future__ import annotations
 
