@@ -17,15 +17,15 @@ void b200_set_error(const char *fmt, ...) {
 // Keep freed stream-ordered allocations in the default memory pool instead of returning them to the driver at every
 // synchronisation: temporaries (projection tables, search structures) are re-allocated for every scene.
 void b200_pool_keep_memory() {
-    static bool done = false;
-    if (done) return;
+    static bool done[64] = {false};  // per device: a process may drive more than one GPU
     int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
     cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ULL;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    done = true;
+    done[dev] = true;
 }
 
 extern "C" const char *b200_version(void) { return "satpy_b200 0.1.0 (sm_100a)"; }
