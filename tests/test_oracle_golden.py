@@ -376,3 +376,34 @@ def test_ll2cr_oracle_is_the_affine_map_of_the_target_area():
     lon2[0, 0] = np.nan
     n2, c2, r2 = oewa.ll2cr(lon2, lat, dst)
     assert n2 == n_in - 1 and np.isnan(c2[0, 0]) and np.isnan(r2[0, 0])
+
+
+def test_observer_look_equals_east_north_up_geometry():
+    """The restated pyorbital ``get_observer_look`` (unpinned in the reference) against textbook geometry: geodetic ->
+    ECEF on WGS84, line of sight in the local east-north-up frame of the observer.  Time drops out (both points rotate
+    with the earth), so any epoch must give the same angles."""
+    a, f = 6378.137, 1.0 / 298.257223563
+    e2 = f * (2.0 - f)
+
+    def ecef(lon, lat, h):
+        lam, phi = np.deg2rad(lon), np.deg2rad(lat)
+        n = a / np.sqrt(1.0 - e2 * np.sin(phi) ** 2)
+        return np.stack([(n + h) * np.cos(phi) * np.cos(lam), (n + h) * np.cos(phi) * np.sin(lam),
+                         (n * (1.0 - e2) + h) * np.sin(phi)], axis=-1)
+
+    rng = np.random.default_rng(12)
+    lon = rng.uniform(-150.0, 0.0, 400)
+    lat = rng.uniform(-70.0, 70.0, 400)
+    sat_lon, sat_lat, sat_alt = -75.2, 0.05, 35786.023
+    d = ecef(sat_lon, sat_lat, sat_alt) - ecef(lon, lat, 0.0)
+    lam, phi = np.deg2rad(lon), np.deg2rad(lat)
+    east = -np.sin(lam) * d[:, 0] + np.cos(lam) * d[:, 1]
+    north = -np.sin(phi) * np.cos(lam) * d[:, 0] - np.sin(phi) * np.sin(lam) * d[:, 1] + np.cos(phi) * d[:, 2]
+    up = np.cos(phi) * np.cos(lam) * d[:, 0] + np.cos(phi) * np.sin(lam) * d[:, 1] + np.sin(phi) * d[:, 2]
+    az_ref = np.rad2deg(np.arctan2(east, north)) % 360.0
+    el_ref = np.rad2deg(np.arcsin(up / np.linalg.norm(d, axis=1)))
+    for when in (dt.datetime(2019, 3, 14, 18), dt.datetime(2024, 7, 1, 3, 21, 40)):
+        az, el = osolar.get_observer_look(sat_lon, sat_lat, sat_alt, when, lon, lat, 0)
+        daz = np.abs(az - az_ref)
+        np.testing.assert_allclose(np.minimum(daz, 360.0 - daz), 0.0, atol=1e-7)
+        np.testing.assert_allclose(el, el_ref, atol=1e-7)
