@@ -233,8 +233,6 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: satpy_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        os.environ.pop("NCCL_DEBUG", None)
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus and rank == 0:
