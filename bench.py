@@ -144,12 +144,8 @@ class CpuSample:
         self.start_time = demo.START_TIME
         src, dst = rp.make_area(sp), rp.make_area(dp)
         n = max(1, int(round(dst.height * CPU_TILE_ROWS_FRAC)))
-        self.tiles = []
-        for frac in CPU_TILE_AT:
-            r0 = min(dst.height - n, int(dst.height * frac))
-            rows = slice(r0, r0 + n)
-            srows = rp.source_rows_for_tile(src, dst, rows, radius)
-            self.tiles.append((rows, srows, np.ascontiguousarray(counts[srows])))
+        self.tiles = [(rows, srows, np.ascontiguousarray(counts[srows]))
+                      for rows, srows in rp.sample_tiles(src, dst, radius, CPU_TILE_ROWS_FRAC, CPU_TILE_AT)]
         self.mpix = sum((t[0].stop - t[0].start) * dst.width for t in self.tiles) / 1e6
         self.describe = (f"{len(self.tiles)} target row tiles of {n} rows at "
                          f"{'/'.join(f'{f:.3f}' for f in CPU_TILE_AT)} of the height ({self.mpix:.1f} Mpix of "

@@ -102,11 +102,14 @@ def fractional_distances(p1, p2, p3, p4, out_x, out_y):
     return t, s
 
 
-def get_bil_info(src, dst, radius_of_influence=50000.0, neighbours=32, dst_rows: slice | None = None, workers=-1):
+def get_bil_info(src, dst, radius_of_influence=50000.0, neighbours=32, dst_rows: slice | None = None, workers=-1,
+                 src_rows: slice | None = None):
     """``(t, s, valid_input_index, index_array)``; ``index_array`` is (N_target, 4), compressed indices,
     columns = upper-left, upper-right, lower-left, lower-right corner.  ``src`` / ``dst``: oracle Area objects
-    (``dst`` must be an area: its projection defines the plane the interpolation happens in)."""
-    slon, slat = src.get_lonlats()
+    (``dst`` must be an area: its projection defines the plane the interpolation happens in).  ``src_rows``: use
+    only that band of source rows (bounded samples of a large source: a target row tile with the source rows that
+    can reach it; ``valid_input_index`` and the compressed indices then refer to the band)."""
+    slon, slat = src.get_lonlats(src_rows)
     dlon, dlat = dst.get_lonlats(dst_rows)
     vin = valid_lonlat(slon, slat)
     n_valid = int(vin.sum())

@@ -59,9 +59,12 @@ def abi_sunz_threaded(counts, band, src: Area, start_time, workers=None):
 
 
 def abi_sunz_nearest(counts, band, src_params, dst_params, start_time, radius, dst_rows: slice | None = None,
-                     src_rows: slice | None = None, workers=-1, timings: dict | None = None):
+                     src_rows: slice | None = None, workers=-1, timings: dict | None = None,
+                     info: dict | None = None):
     """The whole chain; ``dst_rows`` restricts the target to a row window and ``src_rows`` says which source rows
-    ``counts`` covers (bounded CPU samples: a target tile with the band of source rows that can reach it)."""
+    ``counts`` covers (bounded CPU samples: a target tile with the band of source rows that can reach it).
+    ``info``: a dict that receives the intermediate arrays (neighbour info, lon/lat, corrected source data) so that
+    a checker can compare indices as well as values (oracle/compare.py)."""
     src, dst = make_area(src_params), make_area(dst_params)
     t0 = time.perf_counter()
     if src_rows is None:
@@ -79,6 +82,10 @@ def abi_sunz_nearest(counts, band, src_params, dst_params, start_time, radius, d
     if timings is not None:
         for k, v in (("calibrate_sunz", t1 - t0), ("lonlats", t2 - t1), ("search", t3 - t2), ("gather", t4 - t3)):
             timings[k] = timings.get(k, 0.0) + v
+    if info is not None:
+        info.update(valid_input_index=valid_in, valid_output_index=valid_out, index_array=index, src_lons=slon,
+                    src_lats=slat, dst_lons=dlon, dst_lats=dlat, data=data,
+                    src_row0=0 if src_rows is None else (src_rows.start or 0), src_width=src.width)
     return out
 
 
@@ -106,3 +113,17 @@ def source_rows_for_tile(src: Area, dst: Area, dst_rows: slice, radius, col_step
     if hit.size == 0:
         return slice(0, 0)
     return slice(max(0, hit[0] - pad_rows), min(src.height, hit[-1] + 1 + pad_rows))
+
+
+def sample_tiles(src: Area, dst: Area, radius, rows_frac=1.0 / 256.0, at=(1 / 8, 3 / 8, 5 / 8, 7 / 8), n_rows=None):
+    """Bounded sample of a large resampling job for the CPU side: target row tiles of ``rows_frac`` of the height
+    (or ``n_rows`` rows) starting at the fractions ``at`` of the height, each with the band of source rows that can
+    reach it.  Returns ``[(dst_rows, src_rows), ...]`` (slices).  ``bench.py`` times the oracle on these tiles and
+    the parity tests / the bench's parity leg compare the device's rows of the same tiles with the result."""
+    n = max(1, int(round(dst.height * rows_frac))) if n_rows is None else int(n_rows)
+    tiles = []
+    for frac in at:
+        r0 = max(0, min(dst.height - n, int(dst.height * frac)))
+        rows = slice(r0, min(dst.height, r0 + n))
+        tiles.append((rows, source_rows_for_tile(src, dst, rows, radius)))
+    return tiles
