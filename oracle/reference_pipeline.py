@@ -99,7 +99,7 @@ def source_rows_for_tile(src: Area, dst: Area, dst_rows: slice, radius, col_step
         return slice(0, 0)
     margin = np.degrees(radius / nearest.R_EARTH) * 1.05 + 1e-6
     lo, hi = dlat[ok].min() - margin, dlat[ok].max() + margin
-    key = (id(src), col_step)
+    key = (tuple(sorted((k, str(v)) for k, v in src.proj_dict.items())), src.width, src.height, src.area_extent, col_step)
     if key not in _ROW_EXTENT_CACHE:
         x, y = src.proj_vectors()
         _, slat = src.proj.inverse(*np.meshgrid(x[::col_step], y))

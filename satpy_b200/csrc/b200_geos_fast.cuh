@@ -10,9 +10,22 @@
 #include "b200_common.cuh"
 #include "b200_proj.cuh"
 
+// Row constants of the float32 view-vector path (sunz.cu, sunz_fast_kernel).  With c = rg^2 - 1 the discriminant of the
+// ellipsoid intersection is q = 1 - c (a - 1) = A_r - B_r tx^2 = B_r (D_r - tx^2), D_r = A_r / B_r; it cancels towards
+// the limb (q -> 0), so D_r and tx^2 are carried as float32 hi + lo pairs: (Dh - Th) + (Dl - Tl) is accurate to a
+// RELATIVE 1e-7 however small the difference (the hi parts subtract exactly once they are within a factor of two) --
+// 4 FP32 instructions, no FP64 pipe, no conversion.  The (unnormalised) ellipsoid normal is
+// (1 + rg sqrt(q), Yr cy, Zr cz) with the column constants cy = tan x_c, cz = 1 (sweep x) or hypot(1, tan x_c)
+// (sweep y).  c_lo .. c_hi: columns outside this range are certainly off the disk in this row (conservative by a pixel).
+struct GeosRowF {
+    float Dh, Dl, Bq, pad;
+    float Yr, Zr, c_lo, c_hi;
+};
+
 struct GeosFast {
     const double2 *colt;  // [width]  {tan(x_c), hypot(1, tan x_c)}
     const double4 *rowt;  // [height] {tan(y_r), hypot(1, tan y_r), (tan y_r)^2 / (1-es) + 1, unused}
+    const GeosRowF *rowf; // [height]
     double rg, c_geos, inv2, lam0, sin_lam0, cos_lam0;
     int32_t sweep_x, enabled;
 };
@@ -22,7 +35,8 @@ struct GeosTabArg {
 };
 
 static __global__ void __launch_bounds__(256)
-geos_tables_kernel(const __grid_constant__ GeosTabArg A, double2 *__restrict__ colt, double4 *__restrict__ rowt) {
+geos_tables_kernel(const __grid_constant__ GeosTabArg A, double2 *__restrict__ colt, double4 *__restrict__ rowt,
+                   GeosRowF *__restrict__ rowf) {
     const b200_proj_t &P = A.area.proj;
     const int64_t W = A.area.width, H = A.area.height;
     const double inv = 1.0 / (P.a * P.p[0]);  // projection metres -> scan angle
@@ -37,6 +51,25 @@ geos_tables_kernel(const __grid_constant__ GeosTabArg A, double2 *__restrict__ c
             double y = (double)r * -A.area.pixel_size_y + A.area.y_ul;
             double t = tan((y - P.y0) * inv);
             rowt[r] = make_double4(t, hypot(1.0, t), t * t * P.p[5] + 1.0, 0.0);
+            const double c = P.p[2], e_r = t * t * P.p[5];
+            GeosRowF f;
+            const double fa = 1.0 - c * e_r, fb = P.mode == 1 ? c * (1.0 + t * t) : c * (1.0 + e_r);
+            const double fd = fa / fb;
+            f.Dh = (float)fd;
+            f.Dl = (float)(fd - (double)f.Dh);
+            f.Bq = (float)fb;
+            f.pad = 0.0f;
+            if (fd > 0.0) {  // |tan x| <= sqrt(D): the columns this row of the disk can reach, widened by 1.5 pixels
+                const double xr = atan(sqrt(fd)) / inv;
+                f.c_lo = (float)floor((P.x0 - xr - A.area.x_ul) / A.area.pixel_size_x - 1.5);
+                f.c_hi = (float)ceil((P.x0 + xr - A.area.x_ul) / A.area.pixel_size_x + 1.5);
+            } else {
+                f.c_lo = 1e9f;
+                f.c_hi = -1e9f;
+            }
+            f.Yr = (float)(P.mode == 1 ? c * hypot(1.0, t) : c);
+            f.Zr = (float)(c * P.p[5] * t);
+            rowf[r] = f;
         }
     }
 }
@@ -47,20 +80,19 @@ static inline int b200_geos_fast_prepare(const b200_geo_t *geo, GeosFast *F, cud
     if (geo->is_swath || geo->area.proj.kind != B200_PROJ_GEOS) return B200_OK;
     const b200_proj_t &P = geo->area.proj;
     b200_pool_keep_memory();
-    double2 *colt = nullptr;
-    double4 *rowt = nullptr;
-    B200_CUDA(cudaMallocAsync((void **)&colt, (size_t)geo->area.width * sizeof(double2), s));
-    cudaError_t e = cudaMallocAsync((void **)&rowt, (size_t)geo->area.height * sizeof(double4), s);
-    if (e != cudaSuccess) {
-        cudaFreeAsync(colt, s);
-        b200_set_error("geos tables: %s", cudaGetErrorString(e));
-        return B200_ENOMEM;
-    }
+    // one allocation: [colt: width (padded to even) x 16 B][rowt: height x 32 B][rowf: height x 32 B]
+    const size_t wpad = ((size_t)geo->area.width + 1) & ~(size_t)1, h = (size_t)geo->area.height;
+    char *buf = nullptr;
+    B200_CUDA(cudaMallocAsync((void **)&buf, wpad * sizeof(double2) + h * (sizeof(double4) + sizeof(GeosRowF)), s));
+    double2 *colt = reinterpret_cast<double2 *>(buf);
+    double4 *rowt = reinterpret_cast<double4 *>(buf + wpad * sizeof(double2));
+    GeosRowF *rowf = reinterpret_cast<GeosRowF *>(buf + wpad * sizeof(double2) + h * sizeof(double4));
     GeosTabArg A;
     A.area = geo->area;
-    geos_tables_kernel<<<b200_grid_for(geo->area.width + geo->area.height, 256, 8), 256, 0, s>>>(A, colt, rowt);
+    geos_tables_kernel<<<b200_grid_for(geo->area.width + geo->area.height, 256, 8), 256, 0, s>>>(A, colt, rowt, rowf);
     F->colt = colt;
     F->rowt = rowt;
+    F->rowf = rowf;
     F->rg = P.p[1];
     F->c_geos = P.p[2];
     F->inv2 = P.p[5];
@@ -73,10 +105,10 @@ static inline int b200_geos_fast_prepare(const b200_geo_t *geo, GeosFast *F, cud
 }
 
 static inline void b200_geos_fast_release(GeosFast *F, cudaStream_t s) {
-    if (F->colt) cudaFreeAsync((void *)F->colt, s);
-    if (F->rowt) cudaFreeAsync((void *)F->rowt, s);
+    if (F->colt) cudaFreeAsync((void *)F->colt, s);  // colt is the start of the one allocation
     F->colt = nullptr;
     F->rowt = nullptr;
+    F->rowf = nullptr;
     F->enabled = 0;
 }
 

@@ -227,6 +227,252 @@ abi_vis_sunz_kernel(const __grid_constant__ FusedBands B, const __grid_constant_
     }
 }
 
+// =====================================================================================================================
+// The hot configuration -- geostationary area, float32 data, correction only (ALG) -- in float32.
+//
+// Per pixel float32 only: the discriminant q = B_r (D_r - tx^2) of the ellipsoid intersection cancels towards the limb
+// and is formed from float32 hi + lo pairs (relative error of q < 1e-6 everywhere, checked in
+// scripts/sunz_f32_check.py) -- a float64 FMA plus the F64 -> F32 conversion saturated the XU pipe that the three
+// MUFU operations need (ncu: sm__inst_executed_pipe_xu at its peak, 0.38 ms).  With s = sqrt(q) the view vector scaled to the ellipsoid is (vx, vy, vz) =
+// ((1 + rg s), c ..., c ...) / (rg + s); the common factor drops out of cos(sza) = n . sun / |n|, so
+//     X = 1 + rg s,  Y = Yr cy,  Z = Zr cz,  num = sd Z + cd_ca X - cd_sa Y,  n2 = X^2 + Y^2 + Z^2,
+//     1 / cos(sza) = sqrt(n2) / num = n2 rsqrt(n2) rcp(num)                     (3 MUFU, ~20 FP32 instructions)
+// Accuracy against the reference's rounded-angle flow, emulated in numpy float32 with +-2 ulp on every hardware
+// approximation (scripts/sunz_f32_check.py; ABI 1 km and SEVIRI full disks, seven times of day): |d cos(sza)| <=
+// 4.8e-7, 1 / cos(sza) within 2.3e-6 relative above alg_hi = 0.1 -- north_star's bar is 1e-5.  Pixels between alg_lo
+// and alg_hi (the ~84.3 .. 95 degree band around the terminator, where the fall-off is steep) are flagged and redone
+// digit by digit with the reference's flow (sunz_fast_fix, out of line).
+//
+// Layout: a warp owns 256 consecutive columns of one row: lane L works on columns 4L .. 4L+3 and 128 + 4L .. 128 + 4L+3,
+// so that every warp-level access is one contiguous run (8-byte count loads: 256 B; 16-byte float loads / stores:
+// 512 B) -- full 32-byte sectors, no half-used ones.  A CTA (4 warps) owns 1024 columns and walks down a band of
+// rows with its column constants in registers; the row constants (32 B) are one broadcast load per row.
+#define SUNZ_FAST_COLS_PER_CTA 1024
+// ABI reflectance calibration with everything that does not depend on the pixel folded on the host.  The 16-bit count
+// goes to float32 without the conversion unit: PRMT builds the float 2^23 + v from the packed halves and one FADD
+// removes the bias (exact for all 16-bit values; signed counts are biased by 0x8000 first), then the reference's
+// operation order (satpy/readers/core/abi.py:155-173, satpy/readers/abi_l1b.py:133-145,67-69).
+struct SunzFastCal {
+    uint32_t xor_mask;   // 0 (unsigned counts) or 0x80008000 (signed: flip the sign bits of both halves)
+    float bias;          // 8388608 (+ 32768 for signed)
+    float fill_f;        // _FillValue as float (NaN: none)
+    float scale, offset, refl_factor;
+    int32_t scaled;      // scale_factor != 1
+    int32_t pad;
+};
+
+struct SunzFastArg {
+    const void *in[4];   // MODE 0: float32 bands; MODE 1: int16 ABI counts per band
+    float *out[4];
+    SunzFastCal cal[4];
+    b200_abi_cal_t cal_full[4];   // for the out-of-line fix-up path
+    int32_t nbands, rows_per_cta;
+    // per-scene float32 constants (kernel parameters are constant-bank operands: no registers)
+    float rg, sd, cdca, cdsa, alg_hi, alg_lo, below;
+    int32_t method;
+};
+
+__device__ __forceinline__ float sunz_cal_refl(uint32_t w, int half, const SunzFastCal &c) {
+    const uint32_t m = half ? __byte_perm(w, 0x4b000000u, 0x7432) : __byte_perm(w, 0x4b000000u, 0x7410);
+    float f = __fsub_rn(__uint_as_float(m), c.bias);
+    f = (f == c.fill_f) ? __int_as_float(0x7fc00000) : f;
+    const float rad = c.scaled ? __fadd_rn(__fmul_rn(f, c.scale), c.offset) : f;
+    return __fmul_rn(__fmul_rn(rad, c.refl_factor), 100.0f);
+}
+
+__device__ __forceinline__ float sunz_rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float sunz_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sunz_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ uint2 sunz_ld_counts4(const int16_t *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 sunz_ld_float4(const float *p) {
+    const int4 v = ld_stream_v4(p);
+    return make_float4(__int_as_float(v.x), __int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w));
+}
+
+// flagged pixels again, with the reference's rounded-angle flow (k: bit of `flags`, pixel col0 + 128 (k / 4) + k % 4)
+template <int MODE>
+static __device__ __noinline__ void sunz_fast_fix(const SunzFastArg &A, const SunzDev &S, int r, int col0, unsigned flags) {
+    const int64_t W = S.geo.width;
+    while (flags) {
+        const int k = __ffs(flags) - 1;
+        flags &= flags - 1;
+        const int col = col0 + ((k >> 2) << 7) + (k & 3);
+        const float corr = b200_sunz_corr(S, b200_cos_sza_pixel<false, true>(S, S.geo.row0 + r, col));
+        const int64_t i = (int64_t)r * W + col;
+        for (int b = 0; b < A.nbands; ++b) {
+            float v;
+            if (MODE == 1) v = b200_abi_cal_vis((int)static_cast<const int16_t *>(A.in[b])[i], A.cal_full[b]);
+            else v = static_cast<const float *>(A.in[b])[i];
+            A.out[b][i] = __fmul_rn(v, corr);
+        }
+    }
+}
+
+template <int MODE, bool SWEEP_X>
+__global__ void __launch_bounds__(128, 8)
+sunz_fast_kernel(const __grid_constant__ SunzFastArg A, const __grid_constant__ SunzDev S) {
+    const int W = (int)S.geo.width;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col0 = blockIdx.x * SUNZ_FAST_COLS_PER_CTA + warp * 256 + lane * 4;
+    if (col0 >= W) return;                      // W % 4 == 0 (checked by the caller): a group is all in or all out
+    const bool second = col0 + 128 < W;
+    float Th[8], Tl[8], cy[8], cz[8];  // tx^2 (hi, lo), tan x, hypot(1, tan x) of this thread's eight columns
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = min(col0 + ((k >> 2) << 7) + (k & 3), W - 1);
+        const double2 ct = __ldg(S.fast.colt + c);
+        const double T = ct.x * ct.x;
+        Th[k] = (float)T;
+        Tl[k] = (float)(T - (double)Th[k]);
+        cy[k] = (float)ct.x;
+        cz[k] = SWEEP_X ? 1.0f : (float)ct.y;
+    }
+    const float rg = A.rg, sd = A.sd, cdca = A.cdca, cdsa = A.cdsa, alg_hi = A.alg_hi, alg_lo = A.alg_lo, below = A.below;
+    const int method = A.method;
+    const int r_end = min((int)S.geo.nrows, (int)(blockIdx.y + 1) * A.rows_per_cta);
+    const float4 *rowf = reinterpret_cast<const float4 *>(S.fast.rowf + S.geo.row0);
+    for (int r = blockIdx.y * A.rows_per_cta; r < r_end; ++r) {
+        const float4 f0 = __ldg(rowf + 2 * r), f1 = __ldg(rowf + 2 * r + 1);
+        const float Dh = f0.x, Dl = f0.y, Bq = f0.z;
+        const float Yr = f1.x, Zr = f1.y, c_lo = f1.z, c_hi = f1.w;
+        const int64_t base = (int64_t)r * W + col0;
+        // start the loads of the first band's data before the arithmetic (further bands are loaded where they are used)
+        uint2 cnt[2];
+        float4 dat[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            if (g == 1 && !second) break;
+            if (MODE == 1) cnt[g] = sunz_ld_counts4(static_cast<const int16_t *>(A.in[0]) + base + g * 128);
+            else dat[g] = sunz_ld_float4(static_cast<const float *>(A.in[0]) + base + g * 128);
+        }
+        unsigned flags = 0;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            if (g == 1 && !second) break;
+            float corr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const float cg = (float)(col0 + g * 128);
+            if (cg + 3.0f >= c_lo && cg <= c_hi) {   // else: the four pixels are off the disk, factor 0
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * g + j;
+                    const float qf = Bq * __fadd_rn(__fsub_rn(Dh, Th[k]), __fsub_rn(Dl, Tl[k]));
+                    const float s = sunz_sqrt_approx(fmaxf(qf, 0.0f));
+                    const float X = fmaf(rg, s, 1.0f);
+                    const float Y = Yr * cy[k];
+                    const float Z = SWEEP_X ? Zr : Zr * cz[k];
+                    const float num = fmaf(cdca, X, fmaf(-cdsa, Y, sd * Z));
+                    const float n2 = fmaf(X, X, fmaf(Y, Y, Z * Z));
+                    const float rs = sunz_rsqrt_approx(n2);
+                    const float czf = num * rs;
+                    float c;
+                    if (method == 0) {
+                        c = sunz_rcp_approx(czf);
+                    } else {  // Li & Shibata: 24.35 / (2 cz + sqrt(498.5225 cz^2 + 1))
+                        c = 24.35f * sunz_rcp_approx(fmaf(2.0f, czf, sunz_sqrt_approx(fmaf(498.5225f * czf, czf, 1.0f))));
+                    }
+                    const bool on = qf >= 0.0f;
+                    const bool hi = czf > alg_hi, lo = czf < alg_lo;
+                    c = hi ? c : below;
+                    c = on ? c : 0.0f;   // off the disk: cos(sza) is NaN, the reference sets the factor to 0
+                    if (on && !hi && !lo) flags |= 1u << k;
+                    corr[j] = c;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (b >= A.nbands) break;
+                float v0, v1, v2, v3;
+                if (MODE == 1) {
+                    uint2 w = b == 0 ? cnt[g] : sunz_ld_counts4(static_cast<const int16_t *>(A.in[b]) + base + g * 128);
+                    w.x ^= A.cal[b].xor_mask;
+                    w.y ^= A.cal[b].xor_mask;
+                    v0 = sunz_cal_refl(w.x, 0, A.cal[b]);
+                    v1 = sunz_cal_refl(w.x, 1, A.cal[b]);
+                    v2 = sunz_cal_refl(w.y, 0, A.cal[b]);
+                    v3 = sunz_cal_refl(w.y, 1, A.cal[b]);
+                } else {
+                    const float4 d = b == 0 ? dat[g] : sunz_ld_float4(static_cast<const float *>(A.in[b]) + base + g * 128);
+                    v0 = d.x, v1 = d.y, v2 = d.z, v3 = d.w;
+                }
+                st_stream_f4(A.out[b] + base + g * 128, __fmul_rn(v0, corr[0]), __fmul_rn(v1, corr[1]),
+                             __fmul_rn(v2, corr[2]), __fmul_rn(v3, corr[3]));
+            }
+        }
+        if (flags) sunz_fast_fix<MODE>(A, S, r, col0, flags);
+    }
+}
+
+// true: the float32 kernel took the job
+template <int MODE>
+static bool sunz_fast_launch(const SunzDev &S, const void *const *in, float *const *out, const b200_abi_cal_t *cal,
+                             int nbands, cudaStream_t s) {
+    if (!S.fast.enabled || !S.alg || (S.geo.width & 3) || S.geo.width >= (1LL << 30) || S.geo.nrows >= (1LL << 30)) return false;
+    for (int b = 0; b < nbands; ++b)
+        if (((uintptr_t)in[b] & (MODE == 1 ? 7 : 15)) || ((uintptr_t)out[b] & 15)) return false;
+    const int gx = (int)((S.geo.width + SUNZ_FAST_COLS_PER_CTA - 1) / SUNZ_FAST_COLS_PER_CTA);
+    // short row bands: the terminator band costs ~20x a fast pixel and is spatially compact, so the CTAs that meet it
+    // must be many and small or they become the tail of the launch
+    int64_t rpc = 8;
+    int64_t gy = (S.geo.nrows + rpc - 1) / rpc;
+    while (gy > 65535) {
+        rpc *= 2;
+        gy = (S.geo.nrows + rpc - 1) / rpc;
+    }
+    for (int b0 = 0; b0 < nbands; b0 += 4) {
+        SunzFastArg A;
+        memset(&A, 0, sizeof(A));
+        A.nbands = nbands - b0 < 4 ? nbands - b0 : 4;
+        A.rows_per_cta = (int32_t)rpc;
+        A.rg = (float)S.fast.rg;
+        A.sd = (float)S.sin_dec;
+        A.cdca = (float)(S.cos_dec * S.cos_a);
+        A.cdsa = (float)(S.cos_dec * S.sin_a);
+        A.alg_hi = (float)S.alg_hi;
+        A.alg_lo = (float)S.alg_lo;
+        // below alg_lo: masked by max_sza (0) or, without max_sza, the constant correction at the limit
+        A.below = S.has_max ? 0.0f : (float)(S.method == 0 ? 1.0 / S.limit_cos : S.li_lim);
+        A.method = S.method;
+        for (int b = 0; b < A.nbands; ++b) {
+            A.in[b] = in[b0 + b];
+            A.out[b] = out[b0 + b];
+            if (MODE == 1) {
+                const b200_abi_cal_t &c = cal[b0 + b];
+                A.cal_full[b] = c;
+                SunzFastCal &f = A.cal[b];
+                f.xor_mask = c.is_unsigned ? 0u : 0x80008000u;
+                f.bias = c.is_unsigned ? 8388608.0f : 8388608.0f + 32768.0f;
+                f.fill_f = c.has_fill ? (float)(c.is_unsigned ? (c.fill & 0xffff) : c.fill) : nanf("");
+                f.scale = c.scale_factor;
+                f.offset = c.add_offset;
+                f.refl_factor = c.refl_factor;
+                f.scaled = c.scale_factor != 1.0f;
+            }
+        }
+        const dim3 grid(gx, (unsigned)gy);
+        if (S.fast.sweep_x) sunz_fast_kernel<MODE, true><<<grid, 128, 0, s>>>(A, S);
+        else sunz_fast_kernel<MODE, false><<<grid, 128, 0, s>>>(A, S);
+    }
+    return true;
+}
+
 static int fill_sunz(SunzDev &S, const b200_geo_t *geo, const b200_sunz_t *sz, bool need_geo) {
     memset(&S.fast, 0, sizeof(S.fast));
     if (need_geo) {
@@ -268,7 +514,7 @@ static void sunz_enable_alg(SunzDev &S) {
     const double a = S.gmst - S.ra + S.fast.lam0;
     S.cos_a = cos(a);
     S.sin_a = sin(a);
-    S.alg_hi = fmax(0.2, S.limit_cos + 1e-3);
+    S.alg_hi = fmax(0.1, S.limit_cos + 1e-3);
     S.alg_lo = (S.has_max ? fmin(S.max_cos, S.limit_cos) : S.limit_cos) - 1e-3;
     S.alg = 1;
 }
@@ -302,7 +548,18 @@ extern "C" int b200_sunz_correct(const float *data, float *out, int32_t nbands, 
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
     sunz_enable_alg(S);
-    if (S.fast.enabled)
+    bool done = false;
+    if (nbands <= 64 && (band_stride & 3) == 0) {
+        const void *in_p[64];
+        float *out_p[64];
+        for (int b = 0; b < nbands; ++b) {
+            in_p[b] = data + (int64_t)b * band_stride;
+            out_p[b] = out + (int64_t)b * band_stride;
+        }
+        done = sunz_fast_launch<0>(S, in_p, out_p, nullptr, nbands, (cudaStream_t)stream);
+    }
+    if (done) {
+    } else if (S.fast.enabled)
         sunz_correct_kernel<true><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
     else
         sunz_correct_kernel<false><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, S);
@@ -386,7 +643,8 @@ extern "C" int b200_abi_vis_sunz(const int16_t *const *counts, float *const *out
     rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
     if (rc) return rc;
     sunz_enable_alg(S);
-    if (S.fast.enabled) abi_vis_sunz_kernel<true><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
+    if (sunz_fast_launch<1>(S, reinterpret_cast<const void *const *>(counts), out, cal, nbands, (cudaStream_t)stream)) {
+    } else if (S.fast.enabled) abi_vis_sunz_kernel<true><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
     else abi_vis_sunz_kernel<false><<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(B, S);
     b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
