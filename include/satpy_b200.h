@@ -237,12 +237,18 @@ int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, double radiu
  * (geostationary area sources only: the source lattice itself is the index, see csrc/nn_geos.cu;
  * B200_EUNSUPPORTED for other sources), 3 = fixed grid in strict mode (every lattice point of the
  * rigorous search disc is examined; 2 rules most of them out with a local lattice model first).
- * All engines return identical indices. */
+ * All engines return identical indices.
+ * `n_valid` may be NULL: the fixed-grid engine then builds without synchronising the stream (the
+ * count is read back by b200_nn_grid_n_valid when somebody asks); the bucket engine always needs it. */
 int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask, double radius,
-                           uint8_t *valid_input, int64_t *n_valid /* host */,
+                           uint8_t *valid_input, int64_t *n_valid /* host, may be NULL */,
                            b200_nn_grid_t **grid /* host out */, int32_t method, void *stream);
 /* engine actually used by a grid (1 or 2) */
 int b200_nn_grid_method(const b200_nn_grid_t *grid, int32_t *method /* host */);
+/* number of valid source points of a grid (synchronises the grid's stream if it was built with
+ * n_valid == NULL).  `valid_input` of the create call must still be alive then.  Replaces the
+ * implicit `valid_input_index.sum()` of pyresample's get_neighbour_info (kdtree.py:60-95). */
+int b200_nn_grid_n_valid(b200_nn_grid_t *grid, int64_t *n_valid /* host */);
 int b200_nn_grid_destroy(b200_nn_grid_t *grid);
 /* bytes of device memory held by the grid */
 int b200_nn_grid_nbytes(const b200_nn_grid_t *grid, int64_t *nbytes /* host */);
@@ -282,6 +288,17 @@ int b200_native_aggregate_f32(const float *data, float *out, int64_t out_rows, i
                               int32_t fx, void *stream);
 int b200_simulated_green(const float *c01, const float *c02, const float *c03, float *out, int64_t n, float f1,
                          float f2, float f3, void *stream);
+
+/* ---------------------------------------------------------------- assembling a row-tiled image
+ * Multi-GPU decomposition of the target (the reference's analogue is dask chunking of the
+ * target, satpy/resample/base.py:32, which never replicates fill values either): the column span of a row block
+ * that the source can reach follows from the geometry (satpy_b200/parallel.py::block_column_span), so each rank
+ * writes the fill value outside it locally (b200_fill_f32_2d) and only the span crosses NVLink (b200_copy_2d:
+ * cudaMemcpy2DAsync on the copy engines; `dst` may be a peer GPU's image mapped into this process).
+ *   pitch / *_pitch_bytes   distance between consecutive rows (elements / bytes) */
+int b200_fill_f32_2d(float *dst, int64_t pitch, int64_t width, int64_t height, float value, void *stream);
+int b200_copy_2d(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
+                 int64_t width_bytes, int64_t height, void *stream);
 
 /* ---------------------------------------------------------------- bilinear
  * Replaces pyresample XArrayBilinearResampler.get_bil_info / get_sample_from_bil_info as driven by

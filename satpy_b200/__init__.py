@@ -18,14 +18,20 @@ __version__ = "0.1.0"
 ETC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "etc")
 
 
-def register(modifiers: bool = True) -> bool:
+def register(modifiers: bool = False) -> bool:
     """Hook the plug-ins into an installed satpy; returns False when satpy is not importable.
 
     * appends ``satpy_b200.resample`` to ``satpy.resample.base.RESAMPLER_MODULES`` so that
-      ``Scene.resample(area, resampler="b200_nearest")`` resolves (satpy/resample/base.py:77-105);
-    * puts ``satpy_b200/etc`` on satpy's ``config_path`` so that the YAML modifier names
-      (``sunz_corrected``, ``effective_solar_pathlength_corrected``) bind to the device classes
-      (satpy/_config.py:158-173, satpy/composites/config_loader.py:176-183).
+      ``Scene.resample(area, resampler="b200_nearest")`` resolves (satpy/resample/base.py:77-105); the resampler
+      classes are ``pyresample.resampler.BaseResampler`` subclasses whenever pyresample is importable, which is what
+      ``satpy.resample.base.resample`` checks before re-using an instance (base.py:151-156);
+    * ``modifiers=True`` additionally puts ``satpy_b200/etc`` on satpy's ``config_path`` so that the YAML modifier
+      names (``sunz_corrected``, ``effective_solar_pathlength_corrected``, ``sunz_reduced``) bind to the device
+      classes (satpy/_config.py:158-173, satpy/composites/config_loader.py:176-183); those are
+      ``satpy.modifiers.ModifierBase`` subclasses when satpy is importable (``.id`` / ``.attrs`` as the dependency tree
+      reads them, satpy/node.py:163).  Off by default: satpy cannot be installed in the image this package was built
+      in, so the re-binding has only been exercised against stub modules (tests/test_host_cpu.py), never against a
+      real Scene.
     """
     try:
         import satpy

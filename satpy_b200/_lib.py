@@ -102,6 +102,7 @@ SIGNATURES = {
     "b200_nn_grid_create": (C.c_int, [_GEO, _P, C.c_double, _P, C.POINTER(C.c_int64), C.POINTER(_P), _P]),
     "b200_nn_grid_create_ex": (C.c_int, [_GEO, _P, C.c_double, _P, C.POINTER(C.c_int64), C.POINTER(_P), C.c_int32, _P]),
     "b200_nn_grid_method": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "b200_nn_grid_n_valid": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "b200_nn_grid_destroy": (C.c_int, [_P]),
     "b200_nn_grid_nbytes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "b200_nn_query": (C.c_int, [_P, _GEO, C.c_double, _P, _P, _P, _P]),
@@ -112,6 +113,8 @@ SIGNATURES = {
     "b200_native_replicate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "b200_native_aggregate_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
     "b200_simulated_green": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _P]),
+    "b200_fill_f32_2d": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_float, _P]),
+    "b200_copy_2d": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "b200_bil_info": (C.c_int, [_P, _P, _GEO, C.c_double, C.c_int32, _P, _P, _P, _P, _P]),
     "b200_bil_sample_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_float, _P]),
     "b200_ll2cr": (C.c_int, [_GEO, _GEO, _P, _P, C.POINTER(C.c_int64), _P]),

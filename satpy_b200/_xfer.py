@@ -1,0 +1,115 @@
+"""Host <-> device transfers of whole images for the plug-in classes.
+
+The reference never has this problem -- its arrays live in host memory -- but a drop-in that takes numpy arrays in
+and hands numpy arrays back moves every image over PCIe, and for config 5 the result alone is 12.85 GB.  Pageable
+``tensor.cpu().numpy()`` / ``torch.from_numpy(a).cuda()`` run at a fraction of the link rate (the driver stages them
+through a small internal buffer, synchronously), so:
+
+* ``host_empty`` returns a numpy array backed by PAGE-LOCKED memory from PyTorch's caching host allocator (a block is
+  reused once the previous result has been dropped, so steady-state calls do not pay ``cudaHostAlloc``);
+* ``to_host`` copies a device tensor into such an array on a side stream, in row chunks that may start as soon as an
+  event says their rows are complete (the resamplers search the next rows meanwhile);
+* ``to_device`` uploads a pageable numpy array through a small ring of cached pinned buffers, the host memcpy of
+  chunk k + 1 overlapping the DMA of chunk k.
+
+PyTorch is plumbing here (memory, streams, events); no arithmetic happens in this module.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_CHUNK_BYTES = 64 << 20
+_local = threading.local()
+
+
+def _state(torch):
+    st = getattr(_local, "st", None)
+    dev = torch.cuda.current_device()
+    if st is None or st["device"] != dev:
+        st = {"device": dev, "h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(), "ring": None, "ring_events": None}
+        _local.st = st
+    return st
+
+
+def copy_stream():
+    """The side stream device->host copies run on (one per thread and device)."""
+    torch = _lib.require_cuda()
+    return _state(torch)["d2h"]
+
+
+def host_empty(shape, dtype):
+    """``(pinned torch tensor, numpy view of it)``: the numpy array keeps the block alive; when it is dropped the
+    block goes back to PyTorch's pinned-memory cache."""
+    torch = _lib.require_cuda()
+    t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+    return t, t.numpy()
+
+
+def to_host(dev_tensor, after=None, wait=True):
+    """Device tensor -> numpy array in page-locked memory, copied on the side stream after ``after`` (a CUDA event;
+    default: everything queued on the current stream).  ``wait=False`` returns ``(array, done_event)`` at once."""
+    torch = _lib.require_cuda()
+    st = _state(torch)
+    pin, arr = host_empty(dev_tensor.shape, dev_tensor.dtype)
+    if after is None:
+        after = torch.cuda.Event()
+        after.record(torch.cuda.current_stream())
+    s = st["d2h"]
+    s.wait_event(after)
+    with torch.cuda.stream(s):
+        pin.copy_(dev_tensor, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(s)
+    dev_tensor.record_stream(s)
+    if wait:
+        done.synchronize()
+        return arr
+    return arr, done
+
+
+def to_device(array, dtype=None):
+    """Pageable (or pinned) numpy array / CPU tensor -> new CUDA tensor, stream-ordered on the CURRENT stream.
+
+    Chunks of 64 MiB go through a ring of two cached pinned buffers: the host memcpy of one chunk overlaps the DMA of
+    the previous one.  Small arrays take the plain path."""
+    torch = _lib.require_cuda()
+    t = array if isinstance(array, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(array))
+    if t.is_cuda:
+        return t if dtype is None else t.to(dtype)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if t.is_pinned() or nbytes <= (8 << 20):
+        return t.to("cuda", non_blocking=t.is_pinned())
+    st = _state(torch)
+    if st["ring"] is None:
+        st["ring"] = [torch.empty(_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        st["ring_events"] = [None, None]
+    out = torch.empty(t.shape, dtype=t.dtype, device="cuda")
+    src = t.view(-1).view(torch.uint8)
+    dst = out.view(-1).view(torch.uint8)
+    s = st["h2d"]
+    s.wait_stream(torch.cuda.current_stream())     # `out` was allocated on the current stream
+    k = 0
+    for off in range(0, nbytes, _CHUNK_BYTES):
+        n = min(_CHUNK_BYTES, nbytes - off)
+        slot = k & 1
+        ev = st["ring_events"][slot]
+        if ev is not None:
+            ev.synchronize()                        # the DMA that last read this buffer has finished
+        buf = st["ring"][slot][:n]
+        buf.copy_(src[off:off + n])                 # host memcpy (multi-threaded for large copies)
+        with torch.cuda.stream(s):
+            dst[off:off + n].copy_(buf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        st["ring_events"][slot] = ev
+        k += 1
+    torch.cuda.current_stream().wait_stream(s)
+    out.record_stream(s)
+    return out

@@ -110,3 +110,45 @@ extern "C" int b200_area_lonlats(const b200_geo_t *geo, double *lons, double *la
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Assembling a row-tiled image: the part of a row block the source can never reach is known from
+// the geometry, so every rank writes that fill value itself and only the column span that can hold data crosses NVLink.
+__global__ void __launch_bounds__(256)
+fill_f32_2d_kernel(float *__restrict__ dst, int64_t pitch, int64_t width, int64_t height, float value) {
+    // one warp-iteration = 128 consecutive floats of one row (512 B per warp-level store where 16-byte aligned)
+    const int64_t chunks_per_row = (width + 127) >> 7;
+    const int64_t n = chunks_per_row * height;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = warp; it < n; it += nwarps) {
+        const int64_t r = it / chunks_per_row, c0 = (it - r * chunks_per_row) << 7;
+        float *p = dst + r * pitch + c0 + lane * 4;
+        const int64_t left = width - (c0 + lane * 4);
+        if (left >= 4 && (((uintptr_t)p) & 15) == 0) st_stream_f4(p, value, value, value, value);
+        else for (int k = 0; k < 4 && k < left; ++k) st_stream_f1(p + k, value);
+    }
+}
+
+extern "C" int b200_fill_f32_2d(float *dst, int64_t pitch, int64_t width, int64_t height, float value, void *stream) {
+    B200_CHECK_ARG(width >= 0 && height >= 0 && pitch >= width, "bad shape");
+    if (width == 0 || height == 0) return B200_OK;
+    B200_CHECK_ARG(dst != nullptr, "NULL pointer");
+    const int64_t warps = ((width + 127) >> 7) * height;
+    fill_f32_2d_kernel<<<b200_grid_for(warps * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(dst, pitch, width, height, value);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_copy_2d(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
+                            int64_t width_bytes, int64_t height, void *stream) {
+    B200_CHECK_ARG(width_bytes >= 0 && height >= 0 && dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes,
+                   "bad shape");
+    if (width_bytes == 0 || height == 0) return B200_OK;
+    B200_CHECK_ARG(dst != nullptr && src != nullptr, "NULL pointer");
+    // copy engines; dst may be a peer GPU's memory mapped into this process (unified addressing)
+    B200_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes,
+                                (size_t)height, cudaMemcpyDefault, (cudaStream_t)stream));
+    return B200_OK;
+}

@@ -226,7 +226,8 @@ extern "C" int b200_nn_grid_nbytes(const b200_nn_grid_t *grid, int64_t *nbytes) 
     } while (0)
 
 // exclusive prefix sum of the valid mask (raw -> compressed index) and the number of valid points
-static int nn_prefix(b200_nn_grid *g, const uint8_t *valid_input, cudaStream_t s) {
+// lazy: do not read the count back (no host synchronisation); b200_nn_grid_n_valid does it on demand
+static int nn_prefix(b200_nn_grid *g, const uint8_t *valid_input, cudaStream_t s, bool lazy) {
     int rc = B200_OK;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -237,6 +238,11 @@ static int nn_prefix(b200_nn_grid *g, const uint8_t *valid_input, cudaStream_t s
     NN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, vit, g->prefix, (int)g->n_src, s));
     NN_TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
     NN_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, vit, g->prefix, (int)g->n_src, s));
+    g->valid_input = valid_input;
+    if (lazy) {
+        g->n_valid = -1;
+        goto fail;  // (common clean-up)
+    }
     NN_TRY(cudaMemcpyAsync(&last_prefix, g->prefix + g->n_src - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     NN_TRY(cudaMemcpyAsync(&last_valid, valid_input + g->n_src - 1, 1, cudaMemcpyDeviceToHost, s));
     NN_TRY(cudaStreamSynchronize(s));
@@ -247,7 +253,7 @@ fail:
 }
 
 static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask, uint8_t *valid_input,
-                    cudaStream_t s) {
+                    cudaStream_t s, bool lazy_count) {
     int rc = B200_OK;
     const bool bucket = g->mode == B200_NN_BUCKET;
     const int64_t n_src = g->n_src;
@@ -333,7 +339,7 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
             S, mask, valid_input, rec, g->pts32, cell_of, g->band_off, phi0, inv_dphi, nbands, fast);
     NN_TRY(cudaGetLastError());
     b200_geos_fast_release(&fast, s);
-    rc = nn_prefix(g, valid_input, s);
+    rc = nn_prefix(g, valid_input, s, lazy_count && !bucket);
     if (rc) goto fail;
     if (!bucket) {
         g->pts = rec;  // the raw-indexed records ARE the search structure
@@ -372,7 +378,7 @@ extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask
                                       int64_t *n_valid, b200_nn_grid_t **grid, int32_t method, void *stream) {
     int rc = b200_check_geo(src, "b200_nn_grid_create");
     if (rc) return rc;
-    B200_CHECK_ARG(grid != nullptr && n_valid != nullptr, "NULL output argument");
+    B200_CHECK_ARG(grid != nullptr, "NULL output argument");
     B200_CHECK_ARG(valid_input != nullptr, "valid_input is NULL");
     B200_CHECK_ARG(radius > 0.0 && isfinite(radius), "radius_of_influence must be positive and finite");
     B200_CHECK_ARG(method >= 0 && method <= 3, "method must be 0 (auto), 1 (bucket), 2 (fixed grid) or 3 (fixed grid, strict)");
@@ -401,13 +407,30 @@ extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask
     cudaGetDevice(&g->device);
     cudaStream_t s = (cudaStream_t)stream;
     g->stream = stream;
-    rc = nn_build(g, src, mask, valid_input, s);
+    // n_valid == NULL: the caller does not need the count now.  The fixed-grid engine then builds without any host
+    // synchronisation (b200_nn_grid_n_valid reads the count back later); the bucket engine sizes its tables from it.
+    rc = nn_build(g, src, mask, valid_input, s, n_valid == nullptr);
     if (rc) {
         b200_nn_grid_destroy(g);
         return rc;
     }
-    *n_valid = g->n_valid;
+    if (n_valid) *n_valid = g->n_valid;
     *grid = g;
+    return B200_OK;
+}
+
+extern "C" int b200_nn_grid_n_valid(b200_nn_grid_t *grid, int64_t *n_valid) {
+    B200_CHECK_ARG(grid != nullptr && n_valid != nullptr, "NULL argument");
+    if (grid->n_valid < 0) {  // built lazily: read the last prefix entry + the last mask byte back now
+        int32_t last_prefix = 0;
+        uint8_t last_valid = 0;
+        cudaStream_t s = (cudaStream_t)grid->stream;
+        B200_CUDA(cudaMemcpyAsync(&last_prefix, grid->prefix + grid->n_src - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(&last_valid, grid->valid_input + grid->n_src - 1, 1, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaStreamSynchronize(s));
+        grid->n_valid = (int64_t)last_prefix + (last_valid ? 1 : 0);
+    }
+    *n_valid = grid->n_valid;
     return B200_OK;
 }
 

@@ -21,6 +21,7 @@ struct b200_nn_grid {
     int64_t n_src, n_valid;
     double radius;
     int32_t *prefix;  // [n_src] exclusive prefix sum of valid_input: raw -> compressed index
+    const uint8_t *valid_input;  // the caller's mask buffer (needed again only for a lazily read n_valid)
     double4 *pts;     // bucket: [n_valid] records sorted by cell; fixed grid: [n_src] records by raw index
                       // record = {x, y, z, raw index bits}; fixed grid stores x = NaN for invalid pixels
     float4 *pts32;    // fixed grid only: float32 copy {x, y, z, 0} by raw index (distance pre-filter)

@@ -21,16 +21,15 @@ import logging
 
 import numpy as np
 
-from .. import _lib
+from .. import _compat, _lib, _xfer
 from ..dataset import is_dataarray, payload, rewrap
 from ..geometry import as_geometry
 from .astronomy import solar_scalars
 
 logger = logging.getLogger(__name__)
 
-
-class IncompatibleAreas(Exception):
-    """Same role as satpy.composites.core.IncompatibleAreas (composites/core.py:41)."""
+# satpy's own exception type when satpy is importable (its ``except IncompatibleAreas`` clauses then see ours)
+IncompatibleAreas = _compat.incompatible_areas()
 
 
 def _sunz_struct(start_time, limit, max_sza, lonlat_f32, method):
@@ -55,7 +54,7 @@ def _to_cuda_f32(torch, data, allow_f64=False):
         a = np.ascontiguousarray(data)
         if a.dtype not in ok:
             raise TypeError(f"the device sun-zenith correction works on float32/float64 data, got {a.dtype}")
-        return torch.from_numpy(a).to("cuda", non_blocking=True), True
+        return _xfer.to_device(a), True
     if data.dtype not in ((torch.float32, torch.float64) if allow_f64 else (torch.float32,)):
         raise TypeError(f"the device sun-zenith correction works on float32/float64 data, got {data.dtype}")
     return (data if data.is_cuda else data.to("cuda")).contiguous(), False
@@ -116,11 +115,13 @@ def sunz_correct(data, area=None, start_time=None, correction_limit=88.0, max_sz
         fn = lib.b200_sunz_correct_sza_f64 if f64 else lib.b200_sunz_correct_sza
         _lib.check(fn(t.data_ptr(), z.data_ptr(), out.data_ptr(), nbands, h * w, h * w, C.byref(s),
                       _lib.stream_ptr(torch)))
-    return out.cpu().numpy() if was_numpy else out
+    return _xfer.to_host(out) if was_numpy else out
 
 
-class _SunZenithCorrectorBase:
-    """``SunZenithCorrectorBase`` (satpy/modifiers/geometry.py:34-74) without the xarray/dask machinery."""
+class _SunZenithCorrectorBase(_compat.modifier_base()):
+    """``SunZenithCorrectorBase`` (satpy/modifiers/geometry.py:34-74) without the xarray/dask machinery.  A
+    ``satpy.modifiers.ModifierBase`` when satpy is importable (the dependency tree reads ``.id`` and ``.attrs`` of
+    every modifier, satpy/node.py:163), the stand-in of satpy_b200._compat otherwise."""
 
     _method = "cos"
 
@@ -128,7 +129,7 @@ class _SunZenithCorrectorBase:
         self.max_sza = max_sza
         self.max_sza_cos = np.cos(np.deg2rad(max_sza)) if max_sza is not None else None
         # ModifierBase/CompositeBase keep every other keyword (name, prerequisites, _satpy_id, ...) in attrs
-        self.attrs = dict(kwargs)
+        super().__init__(**kwargs)
 
     def _limit(self):
         return 88.0
@@ -163,18 +164,6 @@ class _SunZenithCorrectorBase:
         proj = rewrap(vis, res, attrs=dict(vis.attrs))
         self.apply_modifier_info(vis, proj)
         return proj
-
-    def apply_modifier_info(self, origin, destination):
-        """satpy/composites/core.py:99-125 for the default key set."""
-        o, d = origin.attrs, destination.attrs
-        for k in ("name", "modifiers"):
-            if k == "modifiers" and k in self.attrs:
-                d[k] = self.attrs[k]
-            elif d.get(k) is None:
-                if self.attrs.get(k) is not None:
-                    d[k] = self.attrs[k]
-                elif o.get(k) is not None:
-                    d[k] = o[k]
 
 
 class SunZenithCorrector(_SunZenithCorrectorBase):
@@ -214,7 +203,7 @@ def sunz_reduce(data, sza, limit=55.0, max_sza=90.0, strength=1.5, out=None):
         out = torch.empty_like(t)
     _lib.check(_lib.load().b200_sunz_reduce(t.data_ptr(), z.data_ptr(), out.data_ptr(), nbands, n, n, float(limit),
                                             float(max_sza), float(strength), _lib.stream_ptr(torch)))
-    return out.cpu().numpy() if was_numpy else out
+    return _xfer.to_host(out) if was_numpy else out
 
 
 class SunZenithReducer(_SunZenithCorrectorBase):

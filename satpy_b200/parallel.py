@@ -93,6 +93,67 @@ def source_row_window(src, dst, row0: int, nrows: int, radius: float):
     return first, last - first + 1
 
 
+def block_column_span(src, dst, row0: int, nrows: int, radius: float, align: int = 32):
+    """Columns ``[c_lo, c_hi)`` of target rows [row0, row0 + nrows) that a geostationary source can reach at all;
+    everything outside is fill value whatever the data (the far side of the earth as seen from the satellite).
+
+    The test is the one the search kernel applies before it looks at any source pixel (``nn_fixed_position``,
+    csrc/nn_geos.cu): with (rc, rs) the geocentric radius vector of the target latitude, a target is on the far side
+    when ``rc * cos(lon - lon_0) < 1 / radius_g - 1.5 * radius / a``; here in float64 with 1e-4 of slack, over the row
+    of the block nearest the equator (largest rc).  Only for rectilinear targets (lon depends on the column only:
+    eqc, merc, longlat) and geostationary area sources; any other pair, or a span that wraps around the antimeridian,
+    returns the full width.  ``align``: the span is widened to multiples of ``align`` columns (128-byte rows for the
+    copy engines)."""
+    src, dst = as_geometry(src), as_geometry(dst)
+    width = dst.width
+    full = (0, width)
+    if nrows <= 0:
+        return (0, 0)
+    sp, dp = getattr(src, "proj_dict", None), getattr(dst, "proj_dict", None)
+    if not sp or not dp or sp.get("proj") != "geos" or dp.get("proj") not in ("eqc", "merc", "longlat", "latlong", "latlon", "lonlat"):
+        return full
+    import numpy as np
+    from .geometry import _ellipsoid
+    a, es = _ellipsoid(sp)
+    rg = 1.0 + float(sp["h"]) / a
+    lon0 = math.radians(float(sp.get("lon_0", 0.0)))
+    x, y = dst.get_proj_vectors()
+    y = y[row0:row0 + nrows]
+    kind = dp.get("proj")
+    if kind == "eqc":        # PROJ eqc: x = a lam cos(lat_ts) + x_0, y = a (phi - lat_0) + y_0
+        da, _ = _ellipsoid(dp)
+        lons = np.degrees((x - float(dp.get("x_0", 0.0))) / (da * math.cos(math.radians(float(dp.get("lat_ts", 0.0)))))) \
+            + float(dp.get("lon_0", 0.0))
+        lats = np.degrees((y - float(dp.get("y_0", 0.0))) / da) + float(dp.get("lat_0", 0.0))
+    elif kind in ("longlat", "latlong", "latlon", "lonlat"):
+        lons, lats = x.astype(np.float64), y.astype(np.float64)
+    else:                    # merc: the latitude needs the iterative inverse -- take it from the device
+        _, lats = dst[slice(row0, row0 + nrows), slice(0, 1)].get_lonlats()
+        lons, _ = dst[slice(row0, row0 + 1), slice(0, width)].get_lonlats()
+    lats, lons = np.asarray(lats, dtype=np.float64).ravel(), np.asarray(lons, dtype=np.float64).ravel()
+    ok = np.isfinite(lats) & (np.abs(lats) <= 90.0)
+    if not ok.any() or not np.isfinite(lons).all():
+        return full
+    phi = np.deg2rad(lats[ok])
+    rp2 = 1.0 - es
+    pg = np.arctan(rp2 * np.tan(phi))
+    r = math.sqrt(rp2) / np.sqrt(rp2 * np.cos(pg) ** 2 + np.sin(pg) ** 2)
+    rc = float((r * np.cos(pg)).max())
+    vis_min = 1.0 / rg - 1.5 * radius / a - 1e-5 - 1e-4
+    thr = vis_min / rc
+    if thr > 1.0:
+        return (0, 0)
+    vis = np.cos(np.deg2rad(lons) - lon0) >= thr
+    idx = np.flatnonzero(vis)
+    if idx.size == 0:
+        return (0, 0)
+    if idx.size != idx[-1] - idx[0] + 1:     # two pieces (the disk straddles the antimeridian of the target grid)
+        return full
+    c_lo = (int(idx[0]) // align) * align
+    c_hi = min(width, -(-(int(idx[-1]) + 1) // align) * align)
+    return (c_lo, c_hi)
+
+
 def all_gather_rows(full_image, tile_rows: int, rank: int, group=None):
     """One NCCL all-gather, in place: rank r owns rows [r*tile_rows, (r+1)*tile_rows) of ``full_image``
     (shape ``(world_size * tile_rows, width)``); afterwards every rank holds every tile."""
@@ -165,12 +226,35 @@ class PeerImage:
         self.peers = [self.local if r == self.rank else self.handle.get_buffer(r, tuple(shape), dtype)
                       for r in range(self.world)]
         self.stream = torch.cuda.Stream()
+        self.fill_stream = torch.cuda.Stream()
         self.trace = None  # set to a list to collect (peer, row0, nbytes, start event, end event) per copy
+        self.bytes_pushed = 0   # payload this rank sent since the counter was last reset (bench.py reports it)
 
-    def push_rows(self, row0: int, nrows: int, after=None):
+    def fill_outside(self, blocks, value=float("nan")):
+        """``blocks``: ``[(row0, nrows, (c_lo, c_hi)), ...]`` -- write ``value`` into the columns outside ``[c_lo, c_hi)``
+        of those rows of the LOCAL image (what no peer will send, see ``push_rows(col_span=)``), on a side stream that
+        ``finish()`` joins."""
+        torch = self.torch
+        lib = _lib.load()
+        width = self.local.shape[-1]
+        st = self.fill_stream
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            sp = int(st.cuda_stream)
+            for row0, nrows, (c_lo, c_hi) in blocks:
+                if nrows <= 0:
+                    continue
+                base = self.local[row0]
+                if c_lo > 0:
+                    _lib.check(lib.b200_fill_f32_2d(base.data_ptr(), width, c_lo, nrows, value, sp))
+                if c_hi < width:
+                    _lib.check(lib.b200_fill_f32_2d(base[c_hi:].data_ptr(), width, width - c_hi, nrows, value, sp))
+
+    def push_rows(self, row0: int, nrows: int, after=None, col_span=None):
         """Copy rows [row0, row0 + nrows) of ``local`` into every peer's image (``nrows`` may be 0: the rank still
         takes part in the rounds); ``after``: CUDA event recorded when those rows are complete (default: everything
-        queued on the current stream so far)."""
+        queued on the current stream so far).  ``col_span=(c_lo, c_hi)``: send only those columns (2-D copies on the
+        copy engines, ``b200_copy_2d``); the receivers fill the rest themselves (``fill_outside``)."""
         torch = self.torch
         if self.world == 1:
             return
@@ -180,24 +264,37 @@ class PeerImage:
         st = self.stream
         st.wait_event(after)
         mine = self.local[row0:row0 + nrows]
+        width = self.local.shape[-1]
+        esize = self.local.element_size()
+        c_lo, c_hi = (0, width) if col_span is None else (int(col_span[0]), int(col_span[1]))
+        empty = nrows <= 0 or c_hi <= c_lo
+        nbytes = 0 if empty else nrows * (c_hi - c_lo) * esize
+        lib = _lib.load()
         with torch.cuda.stream(st):
             for k in range(1, self.world):
                 self.handle.barrier(channel=1, timeout_ms=self.BARRIER_TIMEOUT_MS)
-                if nrows <= 0:
+                if empty:
                     continue
                 peer = round_peer(self.rank, k, self.world)
                 if self.trace is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(st)
-                self.peers[peer][row0:row0 + nrows].copy_(mine, non_blocking=True)
+                if c_lo == 0 and c_hi == width:
+                    self.peers[peer][row0:row0 + nrows].copy_(mine, non_blocking=True)
+                else:
+                    _lib.check(lib.b200_copy_2d(self.peers[peer][row0, c_lo:].data_ptr(), width * esize,
+                                                mine[0, c_lo:].data_ptr(), width * esize, (c_hi - c_lo) * esize, nrows,
+                                                int(st.cuda_stream)))
+                self.bytes_pushed += nbytes
                 if self.trace is not None:
                     e1.record(st)
-                    self.trace.append((peer, row0, mine.numel() * mine.element_size(), e0, e1))
+                    self.trace.append((peer, row0, nbytes, e0, e1))
 
     def finish(self):
         """Stream-ordered on the current stream: own copies done, then all ranks' copies done."""
         main = self.torch.cuda.current_stream()
         main.wait_stream(self.stream)
+        main.wait_stream(self.fill_stream)
         if self.world > 1:
             self.handle.barrier(channel=0, timeout_ms=self.BARRIER_TIMEOUT_MS)
         return self.local

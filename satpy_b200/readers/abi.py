@@ -80,11 +80,13 @@ class ABICalibration:
         return s
 
 
-def calibrate_abi(counts, cal: ABICalibration, calibration: str = "radiance", out=None):
+def calibrate_abi(counts, cal: ABICalibration, calibration: str = "radiance", out=None, device=None):
     """int16 counts -> float32 radiance / reflectance [%] / brightness temperature [K].
 
     ``counts``: numpy array or torch tensor (int16; uint16 is reinterpreted).  A
-    numpy input gives a numpy result, a CUDA tensor gives a CUDA tensor.
+    numpy input gives a numpy result, a CUDA tensor gives a CUDA tensor; ``device=True`` keeps the result on the
+    device whatever came in (the next stage -- modifier, resampler -- takes it from there: nothing crosses PCIe
+    between the stages, as nothing is computed between the lazy stages of the reference before ``compute()``).
     """
     torch = _lib.require_cuda()
     if calibration == "counts":
@@ -96,7 +98,8 @@ def calibrate_abi(counts, cal: ABICalibration, calibration: str = "radiance", ou
             a = a.view(np.int16)
         if a.dtype != np.int16:
             raise TypeError(f"ABI counts must be int16/uint16, got {a.dtype}")
-        t = torch.from_numpy(a).to("cuda", non_blocking=True)
+        from .. import _xfer
+        t = _xfer.to_device(a)
     else:
         t = counts.contiguous()
         if t.dtype != torch.int16:
@@ -108,4 +111,9 @@ def calibrate_abi(counts, cal: ABICalibration, calibration: str = "radiance", ou
     s = cal.struct(calibration)
     _lib.check(_lib.load().b200_abi_calibrate(t.data_ptr(), out.data_ptr(), t.numel(), C.byref(s),
                                               _lib.stream_ptr(torch)))
-    return out.cpu().numpy() if was_numpy else out
+    if device is None:
+        device = not was_numpy
+    if device:
+        return out
+    from .. import _xfer
+    return _xfer.to_host(out)

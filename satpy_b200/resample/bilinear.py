@@ -17,7 +17,7 @@ import logging
 
 import numpy as np
 
-from .. import _lib
+from .. import _compat, _lib, _xfer
 from ..dataset import is_dataarray, payload, rewrap
 from ..geometry import AreaDefinition, as_geometry
 from .nearest import SEARCH_METHODS, _Grid
@@ -25,10 +25,12 @@ from .nearest import SEARCH_METHODS, _Grid
 LOG = logging.getLogger(__name__)
 
 
-class B200BilinearResampler:
+class B200BilinearResampler(_compat.resampler_base()):
     """Bilinear interpolation between the four nearest source pixels around each target pixel centre."""
 
     def __init__(self, source_geo_def, target_geo_def):
+        if _compat.resampler_base() is not object:
+            super().__init__(source_geo_def, target_geo_def)
         self.source_geo_def = as_geometry(source_geo_def)
         self.target_geo_def = as_geometry(target_geo_def)
         self._orig_target = target_geo_def
@@ -110,12 +112,12 @@ class B200BilinearResampler:
         _lib.check(_lib.load().b200_bil_sample_f32(tdata.data_ptr(), out.data_ptr(), info["gather_index"].data_ptr(),
                                                    info["bilinear_t"].data_ptr(), info["bilinear_s"].data_ptr(), n_out,
                                                    nbands, src.size, n_out, float(fill_value), _lib.stream_ptr(torch)))
-        res = out.cpu().numpy() if was_numpy else out
+        res = _xfer.to_host(out) if was_numpy else out
         if not is_dataarray(data):
             return res
         attrs = dict(data.attrs)
         attrs["area"] = self._orig_target
-        return rewrap(data, res, dims=tuple(data.dims), attrs=attrs)
+        return rewrap(data, res, dims=tuple(data.dims), attrs=attrs, new_area=self.target_geo_def)
 
     def resample(self, data, cache_dir=None, mask_area=None, **kwargs):
         del mask_area

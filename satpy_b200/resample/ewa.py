@@ -15,7 +15,7 @@ import logging
 
 import numpy as np
 
-from .. import _lib
+from .. import _compat, _lib, _xfer
 from ..dataset import is_dataarray, payload, rewrap
 from ..geometry import AreaDefinition, as_geometry
 
@@ -61,10 +61,12 @@ def scan_bands(height: int, rows_per_scan: int, world_size: int):
     return bands
 
 
-class B200EWAResampler:
+class B200EWAResampler(_compat.resampler_base()):
     """ll2cr + fornav; the accumulation grids live on the device for the duration of ``compute``."""
 
     def __init__(self, source_geo_def, target_geo_def):
+        if _compat.resampler_base() is not object:
+            super().__init__(source_geo_def, target_geo_def)
         self.source_geo_def = as_geometry(source_geo_def)
         self.target_geo_def = as_geometry(target_geo_def)
         self._orig_target = target_geo_def
@@ -145,12 +147,12 @@ class B200EWAResampler:
             _lib.check(lib.b200_fornav_finalize(weights.data_ptr(), accums.data_ptr(), out.data_ptr(), nbands, dst.size,
                                                 C.byref(p), float(fill_value), counts, stream))
             self.valid_counts = list(counts)
-        res = out.cpu().numpy() if was_numpy else out
+        res = _xfer.to_host(out) if was_numpy else out
         if not is_dataarray(data):
             return res
         attrs = dict(data.attrs)
         attrs["area"] = self._orig_target
-        return rewrap(data, res, dims=tuple(data.dims), attrs=attrs)
+        return rewrap(data, res, dims=tuple(data.dims), attrs=attrs, new_area=self.target_geo_def)
 
     def resample(self, data, cache_dir=None, mask_area=None, **kwargs):
         del mask_area

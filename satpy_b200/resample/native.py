@@ -10,13 +10,15 @@ from __future__ import annotations
 
 import numpy as np
 
-from .. import _lib
+from .. import _compat, _lib, _xfer
 from ..dataset import is_dataarray, payload, rewrap
 from ..geometry import as_geometry
 
 
-class B200NativeResampler:
+class B200NativeResampler(_compat.resampler_base()):
     def __init__(self, source_geo_def, target_geo_def):
+        if _compat.resampler_base() is not object:
+            super().__init__(source_geo_def, target_geo_def)
         self.source_geo_def = source_geo_def
         self.target_geo_def = target_geo_def
 
@@ -64,9 +66,9 @@ class B200NativeResampler:
                                                      int(y_size), int(x_size), stream))
         else:
             raise ValueError("Must either expand or reduce in both directions")
-        res = res.cpu().numpy() if was_numpy else res
+        res = _xfer.to_host(res) if was_numpy else res
         if not is_dataarray(data):
             return res
         attrs = dict(data.attrs)
         attrs["area"] = target
-        return rewrap(data, res, dims=tuple(data.dims), attrs=attrs)
+        return rewrap(data, res, dims=tuple(data.dims), attrs=attrs, new_area=target)

@@ -16,6 +16,19 @@ Host-side mirror of ``KDTreeResampler`` (satpy/resample/kdtree.py:26-190) and of
 
 Neighbour info stays resident on the device and is reused for every dataset resampled between the
 same two geometries (the analogue of ``self._index_caches``, kdtree.py:58,140).
+
+``resample()`` chooses the work by what is asked for:
+
+* the FIRST float32 dataset between two geometries (no mask, no ``cache_dir``) runs the fused kernel -- search and
+  gather in one pass, no index array written (``b200_nn_query_gather_f32``; config 5 would otherwise write 12.85 GB of
+  indices it never reads again);
+* a SECOND dataset on the same instance (satpy reuses one resampler for every dataset of a source area,
+  satpy/scene.py:877,899-901) searches once more, this time keeping the raw gather index on the device, and every
+  later dataset is a gather;
+* ``precompute()`` called directly, ``cache_dir`` or ``neighbour_info()`` produce the reference's three arrays.
+
+numpy in -> numpy out (page-locked, copied while the next rows are searched), CUDA tensor in -> CUDA tensor out;
+``to_host=`` / ``out=`` override that.
 """
 from __future__ import annotations
 
@@ -27,7 +40,7 @@ import os
 
 import numpy as np
 
-from .. import _lib
+from .. import _compat, _lib, _xfer, _zarr2
 from ..dataset import is_dataarray, payload, rewrap
 from ..geometry import AreaDefinition, SwathDefinition, as_geometry
 
@@ -89,15 +102,35 @@ class _Grid:
             self.handle = None
 
 
-class B200NearestResampler:
+class B200NearestResampler(_compat.resampler_base()):
     """Nearest-neighbour resampling on one B200."""
 
+    ROW_CHUNKS = 8   # host results: rows are produced in this many bands, each copied out while the next is computed
+    trace = None     # set to a list to collect (stage, start event, end event) of the fused path (bench.py)
+
     def __init__(self, source_geo_def, target_geo_def):
+        if _compat.resampler_base() is not object:
+            super().__init__(source_geo_def, target_geo_def)
         self.source_geo_def = as_geometry(source_geo_def)
         self.target_geo_def = as_geometry(target_geo_def)
         self._orig_target = target_geo_def
         self._index_caches = {}
-        self._current = None
+        self._cur = None
+        self._fused_uses = {}
+        self._last_request = None   # (radius, row_window, method) of the last fused call
+
+    @property
+    def _current(self):
+        """The neighbour info of the last request.  A fused ``resample`` leaves none behind; it is computed when
+        somebody looks (tests, ``neighbour_info()``, ``save_neighbour_info``)."""
+        if self._cur is None and self._last_request is not None:
+            radius, rw, method = self._last_request
+            self.precompute(radius_of_influence=radius, row_window=rw, method=method)
+        return self._cur
+
+    @_current.setter
+    def _current(self, value):
+        self._cur = value
 
     # ------------------------------------------------------------------ precompute
     def _default_radius(self):
@@ -105,17 +138,42 @@ class B200NearestResampler:
         res = [r for r in res if r is not None]
         return max(res) if res else 10000.0
 
+    def _mask_ptr(self, torch, mask):
+        if mask is None:
+            return None, None
+        m = payload(mask)
+        m = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m))
+        if tuple(m.shape) != self.source_geo_def.shape:
+            raise ValueError(f"mask shape {tuple(m.shape)} != source shape {self.source_geo_def.shape}")
+        m = m.to("cuda").to(torch.uint8).contiguous()
+        return m, m.data_ptr()
+
+    def _build_grid(self, torch, radius, method, mask_ptr=None, want_count=True):
+        """``(grid, valid_input, n_valid or None)``: the search structure over the valid source points."""
+        lib = _lib.load()
+        src = self.source_geo_def
+        valid_input = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
+        n_valid = C.c_int64(0)
+        handle = C.c_void_p(None)
+        gs = src.geo_struct()
+        _lib.check(lib.b200_nn_grid_create_ex(C.byref(gs), mask_ptr, radius, valid_input.data_ptr(),
+                                              C.byref(n_valid) if want_count else None, C.byref(handle),
+                                              SEARCH_METHODS[method], _lib.stream_ptr(torch)))
+        return _Grid(handle), valid_input, (int(n_valid.value) if want_count else None)
+
     def precompute(self, mask=None, radius_of_influence=None, epsilon=0, cache_dir=None, row_window=None,
-                   method="auto", **kwargs):
-        """Build the bucket grid over the valid source points and search every target pixel.
+                   method="auto", gather_only=False, **kwargs):
+        """Build the search structure over the valid source points and search every target pixel.
 
         ``row_window=(row0, nrows)`` restricts the search to a band of target rows (row-tiled
-        multi-GPU use); the default is the whole target.  ``epsilon`` is accepted for signature
-        compatibility: the search is always exact (epsilon = 0).  The neighbour info is cached in device
-        memory on this instance; with ``cache_dir`` it is also written to / read from ``nn_lut-<hash>.npz``
-        (the reference's zarr cache, kdtree.py:125-177, with the same array names).  ``method``: ``"auto"`` (fixed-grid
-        search for geostationary area sources, bucket grid otherwise), ``"bucket"`` or ``"fixed_grid"``;
-        both engines return identical indices.
+        multi-GPU use); the default is the whole target.  ``epsilon``: the search is always exact; a non-zero value is
+        accepted (an exact answer satisfies every epsilon) and logged.  The neighbour info is cached in device
+        memory on this instance; with ``cache_dir`` it is also written to / read from ``nn_lut-<hash>.zarr`` in the
+        reference's layout (kdtree.py:125-177).  ``method``: ``"auto"`` (fixed-grid search for geostationary area
+        sources, bucket grid otherwise), ``"bucket"``, ``"fixed_grid"`` or ``"fixed_grid_strict"``; the engines are
+        tested to return identical indices (``fixed_grid`` rules lattice points out with a local model of the grid
+        whose margins are empirical; ``fixed_grid_strict`` examines every point of the rigorous search disc).
+        ``gather_only``: keep just the raw gather index (what ``compute`` needs), not the reference's three arrays.
         """
         del kwargs
         torch = _lib.require_cuda()
@@ -123,6 +181,8 @@ class B200NearestResampler:
         if radius_of_influence is None:
             radius_of_influence = self._default_radius()
         radius = float(radius_of_influence)
+        if epsilon:
+            LOG.debug("epsilon=%s ignored: the device search is exact", epsilon)
         if mask is not None and cache_dir:
             LOG.warning("Mask and cache_dir both provided to nearest resampler. Cached parameters are affected by "
                         "masked pixels. Will not cache results.")   # kdtree.py:69-73
@@ -131,58 +191,59 @@ class B200NearestResampler:
         row0, nrows = (0, dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
         key = (radius, row0, nrows, method)
         if mask is None and key in self._index_caches:
-            self._current = self._index_caches[key]
-            LOG.debug("Reusing device-resident neighbour info")
-            return key
-        if cache_dir and row_window is None:
+            cached = self._index_caches[key]
+            if gather_only or "index_array" in cached:
+                self._cur = cached
+                LOG.debug("Reusing device-resident neighbour info")
+                return key
+        if cache_dir and row_window is None and not gather_only:
             try:
                 self.load_cached_neighbour_info(cache_dir, radius, epsilon)
                 LOG.debug("Read pre-computed kd-tree parameters")
-                self._index_caches[key] = self._current
+                self._index_caches[key] = self._cur
                 return key
             except IOError:
                 LOG.debug("Computing kd-tree parameters")
-        LOG.debug("Computing bucket-grid neighbour info")
-        mask_ptr = None
-        if mask is not None:
-            m = payload(mask)
-            m = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m))
-            if tuple(m.shape) != src.shape:
-                raise ValueError(f"mask shape {tuple(m.shape)} != source shape {src.shape}")
-            m = m.to("cuda").to(torch.uint8).contiguous()
-            mask_ptr = m.data_ptr()
+        LOG.debug("Computing neighbour info on the device")
+        _m, mask_ptr = self._mask_ptr(torch, mask)
         stream = _lib.stream_ptr(torch)
-        valid_input = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
-        n_valid = C.c_int64(0)
-        handle = C.c_void_p(None)
-        gs = src.geo_struct()
-        _lib.check(lib.b200_nn_grid_create_ex(C.byref(gs), mask_ptr, radius, valid_input.data_ptr(),
-                                              C.byref(n_valid), C.byref(handle), SEARCH_METHODS[method], stream))
-        grid = _Grid(handle)
+        grid, valid_input, n_valid = self._build_grid(torch, radius, method, mask_ptr, want_count=not gather_only)
         used = C.c_int32(0)
         _lib.check(lib.b200_nn_grid_method(grid.handle, C.byref(used)))
         gather_index = torch.empty((nrows, dst.width), dtype=torch.int32, device="cuda")
-        index_array = torch.empty((nrows, dst.width), dtype=torch.int32, device="cuda")
-        valid_output = torch.empty((nrows, dst.width), dtype=torch.uint8, device="cuda")
         gd = dst.geo_struct(row0, nrows)
-        _lib.check(lib.b200_nn_query(grid.handle, C.byref(gd), radius, index_array.data_ptr(),
-                                     gather_index.data_ptr(), valid_output.data_ptr(), stream))
-        info = {"valid_input_index": valid_input, "valid_output_index": valid_output, "index_array": index_array,
-                "gather_index": gather_index, "n_valid": int(n_valid.value), "radius": radius,
-                "row_window": (row0, nrows), "method": {1: "bucket", 2: "fixed_grid"}[used.value] + ("_strict" if method == "fixed_grid_strict" else "")}
+        info = {"valid_input_index": valid_input, "gather_index": gather_index, "n_valid": n_valid, "radius": radius,
+                "row_window": (row0, nrows), "requested_method": method,
+                "method": {1: "bucket", 2: "fixed_grid"}[used.value] + ("_strict" if method == "fixed_grid_strict" else "")}
+        if gather_only:
+            _lib.check(lib.b200_nn_query(grid.handle, C.byref(gd), radius, None, gather_index.data_ptr(), None, stream))
+        else:
+            index_array = torch.empty((nrows, dst.width), dtype=torch.int32, device="cuda")
+            valid_output = torch.empty((nrows, dst.width), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.b200_nn_query(grid.handle, C.byref(gd), radius, index_array.data_ptr(),
+                                         gather_index.data_ptr(), valid_output.data_ptr(), stream))
+            info["index_array"] = index_array
+            info["valid_output_index"] = valid_output
         del grid  # the index arrays are the complete persistent state (kdtree.py:179-182)
         if mask is None:
             self._index_caches[key] = info
-        self._current = info
-        if cache_dir and row_window is None:
+        self._cur = info
+        if cache_dir and row_window is None and not gather_only:
             self.save_neighbour_info(cache_dir, radius, epsilon)
         return key
 
     # --------------------------------------------------------------- cache on disk
     def _cache_filename(self, cache_dir, radius, epsilon=0):
-        """``nn_lut-<hash>.npz``: the reference hashes the two geometries and the search keywords into
-        ``nn_lut-<hash>.zarr`` (satpy/resample/kdtree.py:116-123); zarr is not available here, the array names and
-        dims are the reference's (``NN_COORDINATES``)."""
+        """``nn_lut-<hash>.zarr`` (satpy/resample/kdtree.py:116-123,141-147): inside satpy the hash is pyresample's
+        own (``BaseResampler._create_cache_filename``), so that both resamplers name the file alike; stand-alone
+        it is a sha1 over the two geometries and the search keywords."""
+        create = getattr(super(), "_create_cache_filename", None)
+        if create is not None:
+            try:
+                return create(cache_dir, prefix="nn_lut-", mask=None, radius_of_influence=radius, epsilon=epsilon)
+            except Exception:  # noqa: BLE001 -- geometry objects pyresample cannot hash: fall through
+                pass
+
         def describe(geo):
             if isinstance(geo, AreaDefinition):
                 return {"proj": {k: str(v) for k, v in sorted(geo.proj_dict.items())}, "shape": geo.shape,
@@ -192,16 +253,23 @@ class B200NearestResampler:
             return {"swath": hashlib.sha1(np.ascontiguousarray(lo).tobytes() + np.ascontiguousarray(la).tobytes()).hexdigest()}
         key = json.dumps({"src": describe(self.source_geo_def), "dst": describe(self.target_geo_def),
                           "radius_of_influence": radius, "epsilon": epsilon, "neighbours": 1}, sort_keys=True)
-        return os.path.join(cache_dir, "nn_lut-" + hashlib.sha1(key.encode()).hexdigest() + ".npz")
+        return os.path.join(cache_dir, "nn_lut-" + hashlib.sha1(key.encode()).hexdigest() + ".zarr")
 
     def save_neighbour_info(self, cache_dir, radius_of_influence, epsilon=0):
-        """Persist the three index arrays (``save_neighbour_info``, satpy/resample/kdtree.py:158-177)."""
+        """Persist the three index arrays (``save_neighbour_info``, satpy/resample/kdtree.py:158-177) as a zarr-v2
+        store with the reference's names, dims (``NN_COORDINATES``) and dtypes -- ``index_array`` is widened to the
+        reference's int64, misses become ``n_valid`` as pykdtree reports them."""
         if not cache_dir:
             return None
         os.makedirs(cache_dir, exist_ok=True)
         filename = self._cache_filename(cache_dir, float(radius_of_influence), epsilon)
         info = self.neighbour_info()
-        np.savez_compressed(filename, **info)
+        idx = info["index_array"].astype(np.int64)
+        n_valid = int(info["valid_input_index"].sum())
+        idx[idx < 0] = n_valid
+        _zarr2.write_store(filename, {"valid_input_index": (NN_COORDINATES["valid_input_index"], info["valid_input_index"]),
+                                      "valid_output_index": (NN_COORDINATES["valid_output_index"], info["valid_output_index"]),
+                                      "index_array": (NN_COORDINATES["index_array"], idx)})
         LOG.info("Saving kd_tree neighbour info to %s", filename)
         return filename
 
@@ -211,18 +279,24 @@ class B200NearestResampler:
         if not cache_dir:
             raise IOError
         filename = self._cache_filename(cache_dir, float(radius_of_influence), epsilon)
-        if not os.path.exists(filename):
+        if not os.path.isdir(filename):
             raise IOError(f"no cached neighbour info {filename}")
-        with np.load(filename) as fid:
-            self.load_neighbour_info(fid["valid_input_index"], fid["index_array"], fid["valid_output_index"])
-        self._index_caches[(float(radius_of_influence), 0, self.target_geo_def.height, "auto")] = self._current
+        arrays = {name: _zarr2.read_array(filename, name) for name in NN_COORDINATES}
+        self.load_neighbour_info(arrays["valid_input_index"].astype(bool), arrays["index_array"],
+                                 arrays["valid_output_index"].astype(bool))
+        self._index_caches[(float(radius_of_influence), 0, self.target_geo_def.height, "auto")] = self._cur
         return filename
 
     def neighbour_info(self, as_numpy=True):
         """The reference's three cached arrays (names/dims as ``NN_COORDINATES``)."""
-        if self._current is None:
-            raise RuntimeError("precompute() has not been called")
         cur = self._current
+        if cur is None:
+            raise RuntimeError("precompute() has not been called")
+        if "index_array" not in cur:   # searched for gathering only: search again, keeping everything
+            self._index_caches = {k: v for k, v in self._index_caches.items() if v is not cur}
+            self.precompute(radius_of_influence=cur["radius"], row_window=cur["row_window"],
+                            method=cur["requested_method"])
+            cur = self._cur
         out = {"valid_input_index": cur["valid_input_index"].bool(),
                "valid_output_index": cur["valid_output_index"].bool(),
                "index_array": cur["index_array"].unsqueeze(-1)}
@@ -231,7 +305,8 @@ class B200NearestResampler:
         return out
 
     def load_neighbour_info(self, valid_input_index, index_array, valid_output_index=None):
-        """Install cached index arrays (compressed indices, reference layout) without searching."""
+        """Install cached index arrays (compressed indices, reference layout: int64, misses = n_valid or -1) without
+        searching."""
         torch = _lib.require_cuda()
         src, dst = self.source_geo_def, self.target_geo_def
         vi = torch.as_tensor(np.ascontiguousarray(valid_input_index)).to("cuda").to(torch.uint8).contiguous()
@@ -247,30 +322,56 @@ class B200NearestResampler:
                                                          ia.numel(), _lib.stream_ptr(torch)))
         vo = (torch.ones(dst.shape, dtype=torch.uint8, device="cuda") if valid_output_index is None else
               torch.as_tensor(np.ascontiguousarray(valid_output_index)).to("cuda").to(torch.uint8))
-        self._current = {"valid_input_index": vi, "valid_output_index": vo, "index_array": ia, "gather_index": gi,
-                         "n_valid": n_valid, "radius": None, "row_window": (0, dst.height)}
+        self._cur = {"valid_input_index": vi, "valid_output_index": vo, "index_array": ia, "gather_index": gi,
+                         "n_valid": n_valid, "radius": None, "row_window": (0, dst.height), "method": "loaded"}
 
     # --------------------------------------------------------------------- compute
-    def compute(self, data, weight_funcs=None, fill_value=np.nan, with_uncert=False, **kwargs):
-        """``get_sample_from_neighbour_info``: gather ``data`` through the cached indices."""
-        del kwargs, weight_funcs, with_uncert
-        torch = _lib.require_cuda()
-        if self._current is None:
-            raise RuntimeError("precompute() has not been called")
-        arr = payload(data)
+    @staticmethod
+    def _as_device(torch, arr):
+        """``(cuda tensor, was_numpy)``; bool -> uint8 (the kernels move bytes)."""
         was_numpy = not isinstance(arr, torch.Tensor)
-        t = torch.from_numpy(np.ascontiguousarray(arr)) if was_numpy else arr
+        t = _xfer.to_device(arr) if (was_numpy or not arr.is_cuda) else arr
         if t.dtype == torch.bool:
             t = t.to(torch.uint8)
-        t = t.to("cuda", non_blocking=True).contiguous()
+        return t.contiguous(), was_numpy
+
+    def _finish(self, data, out_dev, host_arr, dims=None):
+        res = host_arr if host_arr is not None else out_dev
+        if not is_dataarray(data):
+            return res
+        attrs = dict(data.attrs)
+        attrs["area"] = self._orig_target
+        return rewrap(data, res, dims=tuple(data.dims) if dims is None else dims, attrs=attrs,
+                      new_area=self.target_geo_def)
+
+    def _row_bands(self, nrows, to_host):
+        n = self.ROW_CHUNKS if to_host else 1
+        rows = -(-nrows // max(1, n))
+        return [(r0, min(rows, nrows - r0)) for r0 in range(0, nrows, max(1, rows))]
+
+    def compute(self, data, weight_funcs=None, fill_value=np.nan, with_uncert=False, to_host=None, out=None, **kwargs):
+        """``get_sample_from_neighbour_info``: gather ``data`` through the cached indices.
+
+        ``to_host``: return a numpy array (page-locked; default: when ``data`` is numpy) -- the rows are gathered in
+        ``ROW_CHUNKS`` bands and each band is copied out while the next one is gathered.  ``out``: CUDA tensor to
+        write the result into."""
+        del kwargs, weight_funcs, with_uncert
+        torch = _lib.require_cuda()
+        if self._cur is None:
+            raise RuntimeError("precompute() has not been called")
+        t, was_numpy = self._as_device(torch, payload(data))
+        to_host = was_numpy if to_host is None else bool(to_host)
         src = self.source_geo_def
         if tuple(t.shape[-2:]) != src.shape:
             raise ValueError(f"data shape {tuple(t.shape)} does not end with the source shape {src.shape}")
         lead = tuple(t.shape[:-2])
         nbands = int(np.prod(lead)) if lead else 1
-        gi = self._current["gather_index"]
-        n_out = gi.numel()
-        out = torch.empty(lead + tuple(gi.shape), dtype=t.dtype, device="cuda")
+        gi = self._cur["gather_index"]
+        nrows, width = gi.shape
+        if out is None:
+            out = torch.empty(lead + (nrows, width), dtype=t.dtype, device="cuda")
+        elif tuple(out.shape) != lead + (nrows, width) or out.dtype != t.dtype or not out.is_contiguous():
+            raise ValueError("out must be a contiguous CUDA tensor of the result's shape and dtype")
         elem = t.element_size()
         np_dtype = np.dtype(str(t.dtype).replace("torch.", ""))
         if fill_value is None:
@@ -278,25 +379,36 @@ class B200NearestResampler:
         with np.errstate(invalid="ignore"):
             fill = np.asarray(fill_value).astype(np_dtype)
         fill_buf = (C.c_char * elem).from_buffer_copy(fill.tobytes())
-        _lib.check(_lib.load().b200_nn_gather(t.data_ptr(), out.data_ptr(), gi.data_ptr(), n_out, nbands,
-                                              src.size, n_out, elem, C.cast(fill_buf, C.c_void_p),
-                                              _lib.stream_ptr(torch)))
-        res = out.cpu().numpy() if was_numpy else out
-        if not is_dataarray(data):
-            return res
-        dims = tuple(data.dims)
-        attrs = dict(data.attrs)
-        attrs["area"] = self._orig_target
-        return rewrap(data, res, dims=dims, attrs=attrs)
+        lib = _lib.load()
+        host_t = host_arr = None
+        if to_host:
+            host_t, host_arr = _xfer.host_empty(out.shape, out.dtype)
+            cs = _xfer.copy_stream()
+        out3 = out.reshape(nbands, nrows, width)
+        for r0, n in self._row_bands(nrows, to_host):
+            _lib.check(lib.b200_nn_gather(t.data_ptr(), out3[0, r0].data_ptr(), gi[r0].data_ptr(), n * width, nbands,
+                                          src.size, nrows * width, elem, C.cast(fill_buf, C.c_void_p),
+                                          _lib.stream_ptr(torch)))
+            if to_host:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                cs.wait_event(ev)
+                with torch.cuda.stream(cs):
+                    host_t.reshape(nbands, nrows, width)[:, r0:r0 + n].copy_(out3[:, r0:r0 + n], non_blocking=True)
+        if to_host:
+            out.record_stream(cs)
+            cs.synchronize()
+        return self._finish(data, out, host_arr)
 
     # -------------------------------------------------------------------- resample
-    def resample(self, data, cache_dir=None, mask_area=None, **kwargs):
-        """``BaseResampler.resample``: mask (swaths by default) -> precompute -> compute."""
+    def resample(self, data, cache_dir=None, mask_area=None, to_host=None, out=None, fused=None, **kwargs):
+        """``BaseResampler.resample``: mask (swaths by default) -> precompute -> compute, with the fused single-pass
+        kernel for the first float32 dataset (module docstring).  ``fused=True/False`` forces / forbids it."""
         torch = _lib.require_cuda()
         if mask_area is None and isinstance(self.source_geo_def, SwathDefinition):
             mask_area = True
+        arr = payload(data)
         if mask_area:
-            arr = payload(data)
             t = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(arr))
             t = t.to("cuda")
             if t.dtype.is_floating_point:
@@ -308,44 +420,94 @@ class B200NearestResampler:
             while m.dim() > 2:
                 m = m.all(dim=0)
             kwargs["mask"] = m
+            arr = t
         pre_kw = {k: kwargs[k] for k in ("mask", "radius_of_influence", "epsilon", "row_window", "method")
                   if k in kwargs}
-        self.precompute(cache_dir=cache_dir, **pre_kw)
         comp_kw = {k: v for k, v in kwargs.items() if k not in pre_kw}
-        return self.compute(data, **comp_kw)
+        dtype_name = str(getattr(arr, "dtype", ""))
+        is_f32 = dtype_name in ("float32", "torch.float32")
+        radius = pre_kw.get("radius_of_influence")
+        radius = float(self._default_radius() if radius is None else radius)
+        dst = self.target_geo_def
+        rw = pre_kw.get("row_window")
+        row0, nrows = (0, dst.height) if rw is None else (int(rw[0]), int(rw[1]))
+        key = (radius, row0, nrows, pre_kw.get("method", "auto"))
+        can_fuse = is_f32 and "mask" not in pre_kw and not cache_dir and key not in self._index_caches
+        if fused is None:
+            fused = can_fuse and self._fused_uses.get(key, 0) == 0
+        elif fused and not can_fuse:
+            raise ValueError("fused resampling needs float32 data, no mask, no cache_dir and no cached neighbour info")
+        if fused:
+            self._fused_uses[key] = self._fused_uses.get(key, 0) + 1
+            self._cur, self._last_request = None, (radius, (row0, nrows), pre_kw.get("method", "auto"))
+            return self._resample_fused(data, arr, radius, (row0, nrows), pre_kw.get("method", "auto"),
+                                        comp_kw.get("fill_value", np.nan), to_host, out)
+        full = bool(cache_dir) or "mask" in pre_kw
+        self.precompute(cache_dir=cache_dir, gather_only=not full, **pre_kw)
+        return self.compute(data, to_host=to_host, out=out, **comp_kw)
 
-    def resample_fused(self, data, radius_of_influence, fill_value=np.nan, row_window=None, out=None,
-                       method="auto"):
-        """float32 only: search and gather in one kernel, no index array materialised.
-
-        For one-off resampling of a single dataset ("fused query+gather").
-        """
+    def _resample_fused(self, data, arr, radius, row_window, method, fill_value, to_host, out):
+        """float32 only: search and gather in one kernel, no index array materialised (SURVEY.md section 8d,
+        "fused query+gather"); host results are produced in row bands, each copied out while the next is searched."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         src, dst = self.source_geo_def, self.target_geo_def
-        arr = payload(data)
-        was_numpy = not isinstance(arr, torch.Tensor)
-        t = torch.from_numpy(np.ascontiguousarray(arr)) if was_numpy else arr
+        t, was_numpy = self._as_device(torch, arr)
         if t.dtype != torch.float32:
-            raise TypeError("resample_fused works on float32 data")
-        t = t.to("cuda", non_blocking=True).contiguous()
+            raise TypeError("fused resampling works on float32 data")
+        if tuple(t.shape[-2:]) != src.shape:
+            raise ValueError(f"data shape {tuple(t.shape)} does not end with the source shape {src.shape}")
+        to_host = was_numpy if to_host is None else bool(to_host)
         lead = tuple(t.shape[:-2])
         nbands = int(np.prod(lead)) if lead else 1
-        row0, nrows = (0, dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
-        stream = _lib.stream_ptr(torch)
-        valid_input = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
-        n_valid = C.c_int64(0)
-        handle = C.c_void_p(None)
-        gs = src.geo_struct()
-        _lib.check(lib.b200_nn_grid_create_ex(C.byref(gs), None, float(radius_of_influence), valid_input.data_ptr(),
-                                              C.byref(n_valid), C.byref(handle), SEARCH_METHODS[method], stream))
-        grid = _Grid(handle)
+        row0, nrows = row_window
+        width = dst.width
+        if fill_value is None:
+            fill_value = np.nan
         if out is None:
-            out = torch.empty(lead + (nrows, dst.width), dtype=torch.float32, device="cuda")
-        gd = dst.geo_struct(row0, nrows)
-        _lib.check(lib.b200_nn_query_gather_f32(grid.handle, C.byref(gd), float(radius_of_influence), t.data_ptr(),
-                                                out.data_ptr(), nbands, src.size, nrows * dst.width,
-                                                float(fill_value), stream))
-        torch.cuda.current_stream().synchronize()
-        del grid
-        return out.cpu().numpy() if was_numpy else out
+            out = torch.empty(lead + (nrows, width), dtype=torch.float32, device="cuda")
+        elif tuple(out.shape) != lead + (nrows, width) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 CUDA tensor of the result's shape")
+        if nrows == 0:
+            return self._finish(data, out, _xfer.host_empty(out.shape, out.dtype)[1] if to_host else None)
+        tr = self.trace
+        if tr is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+        grid, _valid_input, _ = self._build_grid(torch, radius, method, None, want_count=False)
+        if tr is not None:
+            ev[1].record()
+        host_t = host_arr = None
+        if to_host:
+            host_t, host_arr = _xfer.host_empty(out.shape, out.dtype)
+            cs = _xfer.copy_stream()
+        out3 = out.reshape(nbands, nrows, width)
+        stream = _lib.stream_ptr(torch)
+        for r0, n in self._row_bands(nrows, to_host):
+            gd = dst.geo_struct(row0 + r0, n)
+            _lib.check(lib.b200_nn_query_gather_f32(grid.handle, C.byref(gd), radius, t.data_ptr(),
+                                                    out3[0, r0].data_ptr(), nbands, src.size, nrows * width,
+                                                    float(fill_value), stream))
+            if to_host:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                cs.wait_event(ev)
+                with torch.cuda.stream(cs):
+                    host_t.reshape(nbands, nrows, width)[:, r0:r0 + n].copy_(out3[:, r0:r0 + n], non_blocking=True)
+        if tr is not None:
+            ev[2].record()
+            tr.append(("build", ev[0], ev[1]))
+            tr.append(("query_gather", ev[1], ev[2]))
+        del grid   # stream-ordered: freed after the queries queued above
+        if to_host:
+            out.record_stream(cs)
+            cs.synchronize()
+        return self._finish(data, out, host_arr)
+
+    def resample_fused(self, data, radius_of_influence, fill_value=np.nan, row_window=None, out=None,
+                       method="auto"):
+        """Always the fused kernel (kept for callers of the first release; ``resample`` picks it by itself)."""
+        dst = self.target_geo_def
+        rw = (0, dst.height) if row_window is None else (int(row_window[0]), int(row_window[1]))
+        res = self._resample_fused(None, payload(data), float(radius_of_influence), rw, method, fill_value, None, out)
+        return res

@@ -192,7 +192,8 @@ def test_c2_tiles_three_bands_match_oracle(at):
     optr = (C.c_void_p * 3)(*[refl[i].data_ptr() for i in range(3)])
     _lib.check(_lib.load().b200_abi_vis_sunz(cptr, optr, cal, 3, C.byref(g), C.byref(sz), _lib.stream_ptr(torch)))
     r = B200NearestResampler(src, dst)
-    out = r.resample(refl, radius_of_influence=radius, fill_value=np.nan, row_window=(rows.start, n)).cpu().numpy()
+    out = r.resample(refl, radius_of_influence=radius, fill_value=np.nan, row_window=(rows.start, n),
+                     fused=False).cpu().numpy()          # one search, three gathers
     raw_gpu = r._current["gather_index"].cpu().numpy()
     for i, b in enumerate(bands):
         info = {}

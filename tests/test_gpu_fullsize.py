@@ -23,7 +23,8 @@ def test_c5_fused_equals_search_then_gather_and_values_come_from_their_index(c5)
     import torch
     src, dst, data = c5
     r = B200NearestResampler(src, dst)
-    two_step = r.resample(data, radius_of_influence=2000.0)
+    r.precompute(radius_of_influence=2000.0)          # the reference's three arrays
+    two_step = r.compute(data)
     info = r._current
     gi = info["gather_index"]
     hit = gi >= 0

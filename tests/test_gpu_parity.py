@@ -762,11 +762,23 @@ def test_nearest_cache_dir_round_trip(tmp_path):
     data = np.random.default_rng(2).uniform(0, 1, size=src.shape).astype(np.float32)
     r1 = B200NearestResampler(src, dst)
     out1 = r1.resample(data, radius_of_influence=60e3, cache_dir=str(tmp_path))
-    files = list(tmp_path.glob("nn_lut-*.npz"))
-    assert len(files) == 1
-    with np.load(files[0]) as fid:
-        assert set(fid.files) == {"valid_input_index", "valid_output_index", "index_array"}
-        assert fid["index_array"].shape == dst.shape + (1,)
+    import json
+    from satpy_b200 import _zarr2
+    files = list(tmp_path.glob("nn_lut-*.zarr"))
+    assert len(files) == 1 and files[0].is_dir()
+    # the reference's layout: a zarr-v2 group, arrays named and dimensioned as NN_COORDINATES, int64 indices whose
+    # misses are n_valid (what pykdtree reports), bool masks (satpy/resample/kdtree.py:20-22,141-177)
+    assert json.load(open(files[0] / ".zgroup")) == {"zarr_format": 2}
+    assert {p.name for p in files[0].iterdir() if p.is_dir()} == {"valid_input_index", "valid_output_index", "index_array"}
+    meta = json.load(open(files[0] / "index_array" / ".zarray"))
+    assert meta["shape"] == list(dst.shape) + [1] and meta["dtype"] == "<i8" and meta["zarr_format"] == 2
+    assert json.load(open(files[0] / "index_array" / ".zattrs"))["_ARRAY_DIMENSIONS"] == ["y2", "x2", "z2"]
+    assert json.load(open(files[0] / "valid_input_index" / ".zarray"))["dtype"] == "|b1"
+    idx = _zarr2.read_array(str(files[0]), "index_array")
+    vin = _zarr2.read_array(str(files[0]), "valid_input_index")
+    info = r1.neighbour_info()
+    np.testing.assert_array_equal(vin, info["valid_input_index"])
+    np.testing.assert_array_equal(np.where(idx == vin.sum(), -1, idx), info["index_array"])
     r2 = B200NearestResampler(src, dst)
     r2.load_cached_neighbour_info(str(tmp_path), 60e3)
     np.testing.assert_array_equal(r2.compute(data), out1)
@@ -776,7 +788,7 @@ def test_nearest_cache_dir_round_trip(tmp_path):
         B200NearestResampler(src, dst).load_cached_neighbour_info(str(tmp_path), 61e3)
     B200NearestResampler(src, dst).resample(data, radius_of_influence=61e3, cache_dir=str(tmp_path),
                                             mask=np.zeros(src.shape, bool))
-    assert len(list(tmp_path.glob("nn_lut-*.npz"))) == 1
+    assert len(list(tmp_path.glob("nn_lut-*.zarr"))) == 1
 
 
 def test_row_blocks_with_source_windows_reassemble_the_full_image():

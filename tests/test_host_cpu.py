@@ -324,3 +324,189 @@ def test_bench_gpu_arm_refuses_to_run_without_cuda():
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stderr + out.stdout)
+
+
+# ----------------------------------------------------------------------------- boundary: stub satpy / pyresample
+def _install_stub_satpy(monkeypatch):
+    """Minimal stand-ins for the satpy / pyresample surface the plug-in touches (neither can be installed here):
+    ``pyresample.resampler.BaseResampler``, ``satpy.modifiers.ModifierBase`` with the ``id`` property the dependency
+    tree reads (satpy/node.py:163), ``satpy.composites.core.IncompatibleAreas``, ``satpy.resample.base`` with
+    ``RESAMPLER_MODULES`` / ``get_all_resampler_classes`` (base.py:77-105), ``satpy.config``."""
+    import importlib
+    import sys
+    import types
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        monkeypatch.setitem(sys.modules, name, m)
+        return m
+
+    class BaseResampler:
+        def __init__(self, source_geo_def, target_geo_def):
+            self.source_geo_def, self.target_geo_def = source_geo_def, target_geo_def
+
+        def _create_cache_filename(self, cache_dir, prefix="", fmt=".zarr", **kwargs):
+            return os.path.join(cache_dir, prefix + "stubhash" + fmt)
+
+    class IncompatibleAreas(Exception):
+        pass
+
+    class ModifierBase:
+        def __init__(self, name, prerequisites=None, optional_prerequisites=None, **kwargs):
+            kwargs.update(name=name, prerequisites=prerequisites or [], optional_prerequisites=optional_prerequisites or [])
+            self.attrs = kwargs
+
+        @property
+        def id(self):  # noqa: A003
+            return self.attrs["_satpy_id"]
+
+        def apply_modifier_info(self, origin, destination):
+            destination.attrs["modifiers"] = self.attrs.get("modifiers")
+
+    class Config(dict):
+        def set(self, **kw):  # noqa: A003
+            self.update(kw)
+
+    pr = mod("pyresample")
+    pr.resampler = mod("pyresample.resampler", BaseResampler=BaseResampler)
+    modules = ["satpy.resample.kdtree"]
+
+    def get_all_resampler_classes():
+        out = {}
+        for name in modules:
+            if name.startswith("satpy_b200"):
+                out.update(importlib.import_module(name).get_resampler_classes())
+        return out
+    sp = mod("satpy", config=Config(config_path=[]))
+    sp.resample = mod("satpy.resample")
+    sp.resample.base = mod("satpy.resample.base", RESAMPLER_MODULES=modules,
+                           get_all_resampler_classes=get_all_resampler_classes)
+    sp.modifiers = mod("satpy.modifiers", ModifierBase=ModifierBase)
+    sp.composites = mod("satpy.composites")
+    sp.composites.core = mod("satpy.composites.core", IncompatibleAreas=IncompatibleAreas)
+    return BaseResampler, ModifierBase, IncompatibleAreas, get_all_resampler_classes
+
+
+def test_register_and_base_classes_against_stub_satpy(monkeypatch):
+    """With satpy / pyresample importable (stubs): ``register()`` runs its whole body, the resampler classes ARE
+    ``BaseResampler``s (the ``isinstance`` check of satpy/resample/base.py:151-156), the modifiers ARE ``ModifierBase``s
+    with a working ``id``, and ``IncompatibleAreas`` is satpy's own exception type."""
+    import importlib
+    import sys
+    BaseResampler, ModifierBase, IncompatibleAreas, get_all = _install_stub_satpy(monkeypatch)
+    saved = {k: sys.modules[k] for k in list(sys.modules) if k == "satpy_b200" or k.startswith("satpy_b200.")}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        pkg = importlib.import_module("satpy_b200")
+        assert pkg.register() is True
+        import satpy
+        from satpy.resample import base
+        assert "satpy_b200.resample" in base.RESAMPLER_MODULES
+        assert satpy.config.get("config_path") == []            # modifiers are opt-in
+        assert pkg.register(modifiers=True) is True
+        assert pkg.ETC_DIR in satpy.config["config_path"]
+        classes = get_all()
+        assert {"b200_nearest", "b200_bilinear", "b200_ewa", "b200_native"} <= set(classes)
+        src = pkg.AreaDefinition("s", "s", "s", {"proj": "geos", "lon_0": 0.0, "h": 35785831.0, "ellps": "WGS84"}, 8, 8,
+                                 (-4e6, -4e6, 4e6, 4e6))
+        dst = pkg.AreaDefinition("d", "d", "d", {"proj": "eqc", "lon_0": 0.0, "ellps": "WGS84"}, 4, 4, (-2e6, -2e6, 2e6, 2e6))
+        for name in ("b200_nearest", "b200_bilinear", "b200_ewa", "b200_native"):
+            r = classes[name](src, dst)
+            assert isinstance(r, BaseResampler), name
+        r = classes["b200_nearest"](src, dst)
+        assert r._cache_filename("/tmp/c", 5000.0).endswith("nn_lut-stubhash.zarr")   # pyresample's own naming
+        mods = importlib.import_module("satpy_b200.modifiers")
+        m = mods.SunZenithCorrector(name="sunz_corrected", prerequisites=[], modifiers=("sunz_corrected",), _satpy_id="ID")
+        assert isinstance(m, ModifierBase) and m.id == "ID" and m.max_sza == 95.0 and m.correction_limit == 88.0
+        assert mods.IncompatibleAreas is IncompatibleAreas
+        red = mods.SunZenithReducer(name="sunz_reduced", _satpy_id="ID2")
+        assert isinstance(red, ModifierBase) and red.id == "ID2"
+    finally:
+        for k in [k for k in sys.modules if k == "satpy_b200" or k.startswith("satpy_b200.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_dataarraylite_rewrap_carries_coordinates():
+    """What ``_update_resampled_coords`` does (satpy/resample/base.py:45-73): non-spatial coordinates and the name are
+    carried over, x / y come from the target area; modifiers (same grid) keep everything."""
+    from satpy_b200 import AreaDefinition, DataArrayLite
+    from satpy_b200.dataset import rewrap
+    dst = AreaDefinition("d", "d", "d", {"proj": "eqc", "lon_0": 0.0, "ellps": "WGS84"}, 5, 4, (-2.5e6, -2e6, 2.5e6, 2e6))
+    src = DataArrayLite(np.zeros((3, 6, 7), np.float32), ("bands", "y", "x"), {"name": "rgb"},
+                        coords={"bands": np.array(["R", "G", "B"]), "x": np.arange(7.0), "y": np.arange(6.0), "crs": "old"},
+                        name="rgb")
+    res = rewrap(src, np.zeros((3, 4, 5), np.float32), attrs={"area": dst}, new_area=dst)
+    assert res.name == "rgb" and list(res.coords["bands"]) == ["R", "G", "B"] and "crs" not in res.coords
+    x, y = dst.get_proj_vectors()
+    np.testing.assert_array_equal(res.coords["x"], x)
+    np.testing.assert_array_equal(res.coords["y"], y)
+    same = rewrap(src, np.ones((3, 6, 7), np.float32))
+    assert set(same.coords) == {"bands", "x", "y", "crs"} and same.name == "rgb"
+    band = rewrap(src, np.zeros((3, 2, 5), np.float32), attrs={}, new_area=dst)   # a row window: no x / y invented
+    assert "x" not in band.coords and "bands" in band.coords
+
+
+def test_zarr2_store_round_trip(tmp_path):
+    """The hand-written zarr-v2 layout (satpy/resample/kdtree.py:158-177 writes it through xarray/zarr): .zgroup,
+    per-array .zarray / .zattrs with _ARRAY_DIMENSIONS, raw C-order chunks named i.j.k; zlib chunks are readable too."""
+    import json
+    import zlib
+    from satpy_b200 import _zarr2
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, 5000, size=(301, 77, 1)).astype(np.int64)
+    vin = rng.random((40, 50)) > 0.3
+    path = str(tmp_path / "nn_lut-x.zarr")
+    old = _zarr2._TARGET_CHUNK_BYTES
+    _zarr2._TARGET_CHUNK_BYTES = 40000
+    try:
+        _zarr2.write_store(path, {"index_array": (("y2", "x2", "z2"), idx), "valid_input_index": (("y1", "x1"), vin)})
+    finally:
+        _zarr2._TARGET_CHUNK_BYTES = old
+    meta = json.load(open(os.path.join(path, "index_array", ".zarray")))
+    assert meta["zarr_format"] == 2 and meta["compressor"] is None and meta["order"] == "C" and meta["dtype"] == "<i8"
+    assert meta["shape"] == [301, 77, 1] and meta["chunks"][1:] == [77, 1] and meta["chunks"][0] < 301
+    assert os.path.exists(os.path.join(path, "index_array", "0.0.0")) and os.path.exists(os.path.join(path, ".zmetadata"))
+    np.testing.assert_array_equal(_zarr2.read_array(path, "index_array"), idx)
+    np.testing.assert_array_equal(_zarr2.read_array(path, "valid_input_index"), vin)
+    assert _zarr2.array_dims(path, "index_array") == ("y2", "x2", "z2")
+    # a zlib-compressed chunk, as another writer might leave it
+    meta["compressor"] = {"id": "zlib", "level": 1}
+    json.dump(meta, open(os.path.join(path, "index_array", ".zarray"), "w"))
+    for f in os.listdir(os.path.join(path, "index_array")):
+        if not f.startswith("."):
+            fn = os.path.join(path, "index_array", f)
+            raw = open(fn, "rb").read()
+            open(fn, "wb").write(zlib.compress(raw, 1))
+    np.testing.assert_array_equal(_zarr2.read_array(path, "index_array"), idx)
+    with pytest.raises(IOError):
+        _zarr2.read_array(path, "nope")
+
+
+def test_block_column_span_is_conservative():
+    """Outside ``block_column_span`` no target pixel has a neighbour (checked against the oracle's search on a
+    down-scaled config 5), and the spans cover well under half of the global grid."""
+    from oracle import nearest as onn
+    from oracle.projections import Area as OArea
+    from satpy_b200 import demo, parallel
+    s_scale, d_scale = 300 / 10848, 1202 / 80150
+    src, dst = demo.make_area("goes_east_abi_f_1km", s_scale), demo.make_area("global_eqc_500m", d_scale)
+    o_src = OArea(*demo.area_params("goes_east_abi_f_1km", s_scale))
+    o_dst = OArea(*demo.area_params("global_eqc_500m", d_scale))
+    radius = 2.5 * 1002 / s_scale
+    vin, _, idx = onn.get_neighbour_info(*o_src.get_lonlats(), *o_dst.get_lonlats(), radius)
+    hit = idx[..., 0] < vin.sum()
+    total = 0
+    for row0 in range(0, dst.height, 37):
+        n = min(37, dst.height - row0)
+        c_lo, c_hi = parallel.block_column_span(src, dst, row0, n, radius)
+        assert c_lo % 32 == 0 and (c_hi % 32 == 0 or c_hi == dst.width)
+        assert not hit[row0:row0 + n, :c_lo].any() and not hit[row0:row0 + n, c_hi:].any()
+        total += (c_hi - c_lo) * n
+    assert hit.mean() < total / dst.size < 0.5
+    # pairs the test does not know: the whole width
+    laea = demo.make_area("euro_laea_1km", 0.05)
+    assert parallel.block_column_span(src, laea, 0, 10, radius) == (0, laea.width)
+    assert parallel.block_column_span(laea, dst, 0, 10, radius) == (0, dst.width)
