@@ -49,6 +49,31 @@ def host_empty(shape, dtype):
     return t, t.numpy()
 
 
+_filler = None
+
+
+def fill_async(host3, bands, value):
+    """Write ``value`` into the columns outside ``[c_lo, c_hi)`` of the given row bands of a page-locked result
+    ``host3`` (bands, rows, width) on a worker thread (PyTorch's CPU fill is multi-threaded and releases the GIL), while
+    the caller queues device work.  ``bands``: ``[(row0, nrows, (c_lo, c_hi)), ...]``.  Returns a future."""
+    global _filler
+    from concurrent.futures import ThreadPoolExecutor
+    if _filler is None:
+        _filler = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200-fill")
+    width = host3.shape[-1]
+
+    def work():
+        for r0, n, (c_lo, c_hi) in bands:
+            if c_hi <= c_lo:
+                host3[:, r0:r0 + n].fill_(value)
+                continue
+            if c_lo > 0:
+                host3[:, r0:r0 + n, :c_lo].fill_(value)
+            if c_hi < width:
+                host3[:, r0:r0 + n, c_hi:].fill_(value)
+    return _filler.submit(work)
+
+
 def to_host(dev_tensor, after=None, wait=True):
     """Device tensor -> numpy array in page-locked memory, copied on the side stream after ``after`` (a CUDA event;
     default: everything queued on the current stream).  ``wait=False`` returns ``(array, done_event)`` at once."""

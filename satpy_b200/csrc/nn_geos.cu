@@ -181,12 +181,13 @@ __device__ __forceinline__ void nn_track(float d, int idx, float &m1, int &i1, f
 // if the leader is more than 1 m inside (outside) the radius it is accepted (rejected) exactly as float64 would.
 // Anything closer than that is re-done by nn_fixed_search_exact.
 #define GEOS_F32_ERR 1.0f
-__device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc, float fr, double tx, double ty,
-                                                     double tz) {
+// need_exact: the float32 ranking is ambiguous -- the caller runs nn_fixed_search_exact with the float64 coordinates.
+__device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc, float fr, float txf, float tyf,
+                                                     float tzf, bool &need_exact) {
+    need_exact = false;
     const float reach = (float)G.max_ring + 1.0f;
     if (!(fc > -reach) || !(fc < (float)G.W + reach) || !(fr > -reach) || !(fr < (float)G.H + reach)) return -1;
     const int c0 = (int)floorf(fc), r0 = (int)floorf(fr);
-    const float txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
     const float inf = __int_as_float(0x7f800000);
     float m1 = inf, m2 = inf;
     int i1 = -1;
@@ -321,7 +322,8 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
         return s1 < G.radius_f ? (long long)i1 : -1;
     }
     GEOS_CNT(5);
-    return nn_fixed_search_exact(G, fc, fr, tx, ty, tz);
+    need_exact = true;
+    return -1;
 }
 
 // atan for scan angles: a full disk stays below tan = 0.16, where the odd series to x^11 is exact to float32
@@ -382,8 +384,11 @@ __global__ void __launch_bounds__(256) nn_fixed_query_kernel(const __grid_consta
             float cpg = u * inv, spg = v * inv;
             float rr = Q.G.rp * rsqrtf(Q.G.rp2 * cpg * cpg + spg * spg);
             float fc, fr;
-            if (nn_fixed_position(Q.G, rr * cpg, rr * spg, s_rel, c_rel, fc, fr))
-                raw = nn_fixed_search(Q.G, fc, fr, tx, ty, tz);
+            if (nn_fixed_position(Q.G, rr * cpg, rr * spg, s_rel, c_rel, fc, fr)) {
+                bool need_exact;
+                raw = nn_fixed_search(Q.G, fc, fr, (float)tx, (float)ty, (float)tz, need_exact);
+                if (need_exact) raw = nn_fixed_search_exact(Q.G, fc, fr, tx, ty, tz);
+            }
         }
         b200_nn_emit(Q.O, Q.G.prefix, i, raw, ok);
     }
@@ -504,7 +509,9 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
                 double tx = B200_R_EARTH * R.cos_phi * Cc.cos_lam;
                 double ty = B200_R_EARTH * R.cos_phi * Cc.sin_lam;
                 double tz = B200_R_EARTH * R.sin_phi;
-                raw = nn_fixed_search(Q.G, fc, fr, tx, ty, tz);
+                bool need_exact;
+                raw = nn_fixed_search(Q.G, fc, fr, (float)tx, (float)ty, (float)tz, need_exact);
+                if (need_exact) raw = nn_fixed_search_exact(Q.G, fc, fr, tx, ty, tz);
             }
             if (FUSED1)
                 st_stream_f1(Q.O.out + i, raw < 0 ? Q.O.fill : __ldg(Q.O.data + raw));

@@ -118,6 +118,7 @@ class B200NearestResampler(_compat.resampler_base()):
         self._cur = None
         self._fused_uses = {}
         self._last_request = None   # (radius, row_window, method) of the last fused call
+        self.last_d2h_bytes = 0
 
     @property
     def _current(self):
@@ -344,8 +345,49 @@ class B200NearestResampler(_compat.resampler_base()):
         return rewrap(data, res, dims=tuple(data.dims) if dims is None else dims, attrs=attrs,
                       new_area=self.target_geo_def)
 
+    def _host_plan(self, torch, out, row0, nrows, radius, fill_value):
+        """Page-locked result + the plan for filling it: row bands, the column span of each band that the source can
+        reach (satpy_b200.parallel.block_column_span) -- only that crosses PCIe; the rest of each band is the fill
+        value, written by host threads while the device works."""
+        from .. import parallel
+        host_t, host_arr = _xfer.host_empty(out.shape, out.dtype)
+        width = out.shape[-1]
+        bands = []
+        for r0, n in self._row_bands(nrows, True):
+            span = (0, width)
+            if radius is not None and out.dtype == torch.float32:
+                span = parallel.block_column_span(self.source_geo_def, self.target_geo_def, row0 + r0, n, radius)
+            bands.append((r0, n, span))
+        h3 = host_t.reshape(-1, nrows, width)
+        fut = _xfer.fill_async(h3, [(r0, n, sp) for r0, n, sp in bands if sp != (0, width)], fill_value)
+        # bytes that actually cross PCIe for this result (bench.py reports them)
+        self.last_d2h_bytes = int(sum(n * max(0, sp[1] - sp[0]) for _, n, sp in bands) * h3.shape[0] * out.element_size())
+        return host_t, host_arr, h3, bands, fut
+
+    @staticmethod
+    def _band_to_host(torch, cs, h3, out3, r0, n, span):
+        """Queue the device->host copy of one finished row band (its reachable columns) on the copy stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        cs.wait_event(ev)
+        c_lo, c_hi = span
+        if c_hi <= c_lo:
+            return
+        width = out3.shape[-1]
+        with torch.cuda.stream(cs):
+            if (c_lo, c_hi) == (0, width):
+                h3[:, r0:r0 + n].copy_(out3[:, r0:r0 + n], non_blocking=True)
+            else:
+                esize = out3.element_size()
+                lib = _lib.load()
+                for b in range(out3.shape[0]):
+                    _lib.check(lib.b200_copy_2d(h3[b, r0, c_lo:].data_ptr(), width * esize, out3[b, r0, c_lo:].data_ptr(),
+                                                width * esize, (c_hi - c_lo) * esize, n, int(cs.cuda_stream)))
+
     def _row_bands(self, nrows, to_host):
-        n = self.ROW_CHUNKS if to_host else 1
+        width = self.target_geo_def.width
+        # bands start on 16-byte boundaries of the index / output rows; small results are not worth splitting
+        n = self.ROW_CHUNKS if (to_host and width % 4 == 0 and nrows * width >= (1 << 22)) else 1
         rows = -(-nrows // max(1, n))
         return [(r0, min(rows, nrows - r0)) for r0 in range(0, nrows, max(1, rows))]
 
@@ -357,6 +399,9 @@ class B200NearestResampler(_compat.resampler_base()):
         write the result into."""
         del kwargs, weight_funcs, with_uncert
         torch = _lib.require_cuda()
+        if self._cur is None and self._last_request is not None:   # the last request ran fused: search now, keep the index
+            radius, rw, method = self._last_request
+            self.precompute(radius_of_influence=radius, row_window=rw, method=method, gather_only=True)
         if self._cur is None:
             raise RuntimeError("precompute() has not been called")
         t, was_numpy = self._as_device(torch, payload(data))
@@ -380,24 +425,25 @@ class B200NearestResampler(_compat.resampler_base()):
             fill = np.asarray(fill_value).astype(np_dtype)
         fill_buf = (C.c_char * elem).from_buffer_copy(fill.tobytes())
         lib = _lib.load()
-        host_t = host_arr = None
+        host_arr = None
+        bands = [(r0, n, (0, width)) for r0, n in self._row_bands(nrows, False)]
         if to_host:
-            host_t, host_arr = _xfer.host_empty(out.shape, out.dtype)
+            cur = self._cur
+            host_t, host_arr, h3, bands, fut = self._host_plan(torch, out, cur["row_window"][0], nrows,
+                                                               cur.get("radius") if np_dtype == np.float32 else None,
+                                                               float(fill) if np_dtype.kind == "f" else 0)
             cs = _xfer.copy_stream()
         out3 = out.reshape(nbands, nrows, width)
-        for r0, n in self._row_bands(nrows, to_host):
+        for r0, n, span in bands:
             _lib.check(lib.b200_nn_gather(t.data_ptr(), out3[0, r0].data_ptr(), gi[r0].data_ptr(), n * width, nbands,
                                           src.size, nrows * width, elem, C.cast(fill_buf, C.c_void_p),
                                           _lib.stream_ptr(torch)))
             if to_host:
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream())
-                cs.wait_event(ev)
-                with torch.cuda.stream(cs):
-                    host_t.reshape(nbands, nrows, width)[:, r0:r0 + n].copy_(out3[:, r0:r0 + n], non_blocking=True)
+                self._band_to_host(torch, cs, h3, out3, r0, n, span)
         if to_host:
             out.record_stream(cs)
             cs.synchronize()
+            fut.result()
         return self._finish(data, out, host_arr)
 
     # -------------------------------------------------------------------- resample
@@ -477,23 +523,20 @@ class B200NearestResampler(_compat.resampler_base()):
         grid, _valid_input, _ = self._build_grid(torch, radius, method, None, want_count=False)
         if tr is not None:
             ev[1].record()
-        host_t = host_arr = None
+        host_arr = None
+        bands = [(r0, n, (0, width)) for r0, n in self._row_bands(nrows, False)]
         if to_host:
-            host_t, host_arr = _xfer.host_empty(out.shape, out.dtype)
+            host_t, host_arr, h3, bands, fut = self._host_plan(torch, out, row0, nrows, radius, float(fill_value))
             cs = _xfer.copy_stream()
         out3 = out.reshape(nbands, nrows, width)
         stream = _lib.stream_ptr(torch)
-        for r0, n in self._row_bands(nrows, to_host):
+        for r0, n, span in bands:
             gd = dst.geo_struct(row0 + r0, n)
             _lib.check(lib.b200_nn_query_gather_f32(grid.handle, C.byref(gd), radius, t.data_ptr(),
                                                     out3[0, r0].data_ptr(), nbands, src.size, nrows * width,
                                                     float(fill_value), stream))
             if to_host:
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream())
-                cs.wait_event(ev)
-                with torch.cuda.stream(cs):
-                    host_t.reshape(nbands, nrows, width)[:, r0:r0 + n].copy_(out3[:, r0:r0 + n], non_blocking=True)
+                self._band_to_host(torch, cs, h3, out3, r0, n, span)
         if tr is not None:
             ev[2].record()
             tr.append(("build", ev[0], ev[1]))
@@ -502,6 +545,7 @@ class B200NearestResampler(_compat.resampler_base()):
         if to_host:
             out.record_stream(cs)
             cs.synchronize()
+            fut.result()
         return self._finish(data, out, host_arr)
 
     def resample_fused(self, data, radius_of_influence, fill_value=np.nan, row_window=None, out=None,
