@@ -190,7 +190,7 @@ def run_reference(args):
             "config": config_dict(sp, dp, radius, args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample.describe},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def effective_subtiles(args, exchange=None):
@@ -557,7 +557,7 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": sample.mpix / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": sample.describe, "seconds": dt, "stage_seconds": tm}
         line["parity"] = parity_of_tiles(torch, sample, infos, src, dst, full, radius)
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -671,8 +671,32 @@ def timed_local(torch, fn, steps):
     return e0.elapsed_time(e1) / max(1, steps)
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """Rank 0 prints exactly ONE line on stdout.  Libraries that write to the C-level stdout (NCCL prints its version
+    banner there when NCCL_DEBUG is set, whatever NCCL_DEBUG_FILE says) are sent to stderr: file descriptor 1 is
+    duplicated for the JSON line and then pointed at stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    text = json.dumps(obj) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text.encode())
+
+
 def main():
     args = parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -50,28 +50,55 @@ def host_empty(shape, dtype):
 
 
 _filler = None
+_FILL_THREADS = None
+
+
+def _fill_threads():
+    """Host threads for ``fill_async``: the cores this process may use, shared between the ranks of one box, at most 16
+    (``torch.set_num_threads`` / OMP_NUM_THREADS do not matter: torchrun pins them to 1)."""
+    global _FILL_THREADS
+    if _FILL_THREADS is None:
+        import os
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        _FILL_THREADS = max(1, min(16, cores // local_world))
+    return _FILL_THREADS
 
 
 def fill_async(host3, bands, value):
     """Write ``value`` into the columns outside ``[c_lo, c_hi)`` of the given row bands of a page-locked result
-    ``host3`` (bands, rows, width) on a worker thread (PyTorch's CPU fill is multi-threaded and releases the GIL), while
-    the caller queues device work.  ``bands``: ``[(row0, nrows, (c_lo, c_hi)), ...]``.  Returns a future."""
+    ``host3`` (bands, rows, width) on worker threads (PyTorch's CPU fill releases the GIL), while the caller queues
+    device work.  ``bands``: ``[(row0, nrows, (c_lo, c_hi)), ...]``.  Returns an object with ``.result()``."""
     global _filler
     from concurrent.futures import ThreadPoolExecutor
+    nthreads = _fill_threads()
     if _filler is None:
-        _filler = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200-fill")
+        _filler = ThreadPoolExecutor(max_workers=nthreads, thread_name_prefix="b200-fill")
     width = host3.shape[-1]
 
-    def work():
-        for r0, n, (c_lo, c_hi) in bands:
-            if c_hi <= c_lo:
-                host3[:, r0:r0 + n].fill_(value)
-                continue
-            if c_lo > 0:
-                host3[:, r0:r0 + n, :c_lo].fill_(value)
-            if c_hi < width:
-                host3[:, r0:r0 + n, c_hi:].fill_(value)
-    return _filler.submit(work)
+    def work(r0, n, c_lo, c_hi):
+        if c_hi <= c_lo:
+            host3[:, r0:r0 + n].fill_(value)
+            return
+        if c_lo > 0:
+            host3[:, r0:r0 + n, :c_lo].fill_(value)
+        if c_hi < width:
+            host3[:, r0:r0 + n, c_hi:].fill_(value)
+    futures = []
+    for r0, n, (c_lo, c_hi) in bands:
+        step = max(1, -(-n // nthreads))
+        for q in range(r0, r0 + n, step):
+            futures.append(_filler.submit(work, q, min(step, r0 + n - q), c_lo, c_hi))
+
+    class _All:
+        @staticmethod
+        def result():
+            for f in futures:
+                f.result()
+    return _All()
 
 
 def to_host(dev_tensor, after=None, wait=True):
