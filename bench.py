@@ -305,9 +305,11 @@ def run_b200(args):
              for (r0, n) in blocks_all]
     others = [(b * block_rows, blocks_all[b][1], spans[b]) for b in range(world * nsub) if b % world != rank]
     if exchange == "p2p":
-        # cheapest blocks first (narrow spans: high latitudes): the first exchange round starts early
-        blocks.sort(key=lambda blk: (spans[blk.b][1] - spans[blk.b][0]) * blk.nrows)
-        # every rank takes part in every round: same number of pushes, in block-rank order of cost
+        # widest spans first: their pushes (most of the payload) overlap the search of the blocks that follow, and the
+        # blocks that are searched last (high latitudes: narrow or empty spans) leave almost nothing to send after the
+        # last kernel.  Every rank holds one block of every latitude group, so the k-th pushes of all ranks are of
+        # similar size and the lock-step rounds stay balanced.
+        blocks.sort(key=lambda blk: (spans[blk.b][1] - spans[blk.b][0]) * blk.nrows, reverse=True)
     comm_stream = torch.cuda.Stream(priority=-1) if exchange == "nccl" else None   # the exchange gets SMs first
     sunz = SunZenithCorrector(name="sunz_corrected", modifiers=("sunz_corrected",))
     attrs0 = {"start_time": demo.START_TIME, "name": BAND, "calibration": "reflectance", "units": "%",

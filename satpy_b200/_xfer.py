@@ -68,6 +68,36 @@ def _fill_threads():
     return _FILL_THREADS
 
 
+_FILL_GBS = None
+PCIE_GBS = 50.0   # what one GPU's device->host copies reach on this pool (bench.py: 12.85 GB in 257 ms)
+
+
+def fill_rate_gbs():
+    """Measured once: how fast this process' fill threads write page-locked memory (GB/s)."""
+    global _FILL_GBS
+    if _FILL_GBS is None:
+        import time
+        torch = _lib.require_cuda()
+        n = _fill_threads()
+        probe = torch.empty((1, 64 * n, 1 << 18), dtype=torch.float32, pin_memory=True)   # 64 MiB per thread
+        fill_async(probe, [(0, 64 * n, (0, 0))], 0.0).result()
+        t0 = time.perf_counter()
+        fill_async(probe, [(0, 64 * n, (0, 0))], 1.0).result()
+        _FILL_GBS = probe.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    return _FILL_GBS
+
+
+def spans_pay_off(total_bytes, span_bytes):
+    """Copy only the reachable column spans and let host threads write the fill value elsewhere, or copy everything?
+    Spans win when the host can write the rest faster than PCIe would have carried it (one GPU on a many-core host);
+    with several ranks sharing the host's cores and memory bandwidth the plain copy wins, each GPU has its own link."""
+    if span_bytes >= total_bytes:
+        return False
+    full = total_bytes / PCIE_GBS
+    partial = max(span_bytes / PCIE_GBS, (total_bytes - span_bytes) / max(1e-3, fill_rate_gbs()))
+    return partial < 0.8 * full
+
+
 def fill_async(host3, bands, value):
     """Write ``value`` into the columns outside ``[c_lo, c_hi)`` of the given row bands of a page-locked result
     ``host3`` (bands, rows, width) on worker threads (PyTorch's CPU fill releases the GIL), while the caller queues

@@ -359,6 +359,9 @@ class B200NearestResampler(_compat.resampler_base()):
                 span = parallel.block_column_span(self.source_geo_def, self.target_geo_def, row0 + r0, n, radius)
             bands.append((r0, n, span))
         h3 = host_t.reshape(-1, nrows, width)
+        total = nrows * width
+        if not _xfer.spans_pay_off(total, sum(n * max(0, sp[1] - sp[0]) for _, n, sp in bands)):
+            bands = [(r0, n, (0, width)) for r0, n, _ in bands]
         fut = _xfer.fill_async(h3, [(r0, n, sp) for r0, n, sp in bands if sp != (0, width)], fill_value)
         # bytes that actually cross PCIe for this result (bench.py reports them)
         self.last_d2h_bytes = int(sum(n * max(0, sp[1] - sp[0]) for _, n, sp in bands) * h3.shape[0] * out.element_size())
