@@ -331,13 +331,20 @@ def run_b200(args):
         blk.d2h_bytes = rs.last_d2h_bytes
         return res.data
 
+    block_done = None   # diagnostics (B200_TRACE_EXCHANGE): [(block, event after its last kernel)]
+
     def step():
+        nonlocal block_done
         main = torch.cuda.current_stream()
         works = []
         if exchange == "p2p":
             peer_image.fill_outside(others, nan)
         for blk in blocks:
             plugin_block(blk, blk.counts_dev, False)
+            if block_done is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(main)
+                block_done.append((blk.b, e))
             if exchange == "p2p":
                 peer_image.push_rows(blk.slot0, blk.nrows, col_span=spans[blk.b])
             elif exchange == "nccl":
@@ -387,7 +394,7 @@ def run_b200(args):
     clocks = sampler.stop() if sampler else None
     launches = LAUNCHES_PER_BLOCK * sum(1 for blk in blocks if blk.nrows and blk.s_nrows)
     if exchange == "p2p":
-        launches += sum((1 if sp_[0] > 0 else 0) + (1 if sp_[1] < dst.width else 0) for (_, n_, sp_) in others if n_ > 0)
+        launches += 1   # fill_f32_rects_kernel: the fill value outside the spans of the other ranks' blocks
     n_out_total = dst.width * dst.height
     value = n_out_total / 1e6 / (ms_step / 1e3)
 
@@ -397,9 +404,17 @@ def run_b200(args):
         torch.cuda.synchronize()
         dist.barrier()
         peer_image.trace = [] if rank == 0 else None
+        block_done = [] if rank == 0 else None
         t0.record()
         step()
+        t1 = torch.cuda.Event(enable_timing=True)
+        t1.record()
         torch.cuda.synchronize()
+        for b, e in (block_done or []):
+            print(f"block {b} (span {spans[b]}) searched at {t0.elapsed_time(e):7.2f} ms", file=sys.stderr)
+        if rank == 0:
+            print(f"step complete at {t0.elapsed_time(t1):7.2f} ms", file=sys.stderr)
+        block_done = None
         for peer, row0, nbytes, e0, e1 in (peer_image.trace or []):
             print(f"push to {peer} rows {row0}: start {t0.elapsed_time(e0):7.2f} ms, {e0.elapsed_time(e1):6.2f} ms, "
                   f"{nbytes / max(1e-9, e0.elapsed_time(e1)) / 1e6:6.0f} GB/s", file=sys.stderr)

@@ -297,6 +297,8 @@ int b200_simulated_green(const float *c01, const float *c02, const float *c03, f
  * cudaMemcpy2DAsync on the copy engines; `dst` may be a peer GPU's image mapped into this process).
  *   pitch / *_pitch_bytes   distance between consecutive rows (elements / bytes) */
 int b200_fill_f32_2d(float *dst, int64_t pitch, int64_t width, int64_t height, float value, void *stream);
+/* the same for `n` rectangles {row0, nrows, col0, ncols} (host array of 4 n int64) of one image, 64 per launch */
+int b200_fill_f32_rects(float *img, int64_t pitch, const int64_t *rects, int32_t n, float value, void *stream);
 int b200_copy_2d(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
                  int64_t width_bytes, int64_t height, void *stream);
 

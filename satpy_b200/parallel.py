@@ -225,8 +225,20 @@ class PeerImage:
         self.handle = symm_mem.rendezvous(self.local, self.group)
         self.peers = [self.local if r == self.rank else self.handle.get_buffer(r, tuple(shape), dtype)
                       for r in range(self.world)]
-        self.stream = torch.cuda.Stream()
-        self.fill_stream = torch.cuda.Stream()
+        # High priority: the device-side barrier that opens every round is a (tiny) kernel, and the block scheduler
+        # hands free CTA slots to the oldest kernel of equal priority first -- behind a running search kernel with
+        # thousands of CTAs still to dispatch, a barrier waited 0.5 - 2 ms and the rounds trailed the computation
+        # (trace: 12 pushes of 0.47 ms spread over 10.5 ms).  With priority the barrier takes the next slot that frees.
+        self.stream = torch.cuda.Stream(priority=-1)
+        self.fill_stream = torch.cuda.Stream(priority=-1)
+        # "burst" mode (B200_EXCHANGE_MODE=burst; the default from 8 ranks on): one barrier per push, then the copies
+        # to all peers at once on their own streams -- every rank sends 1/(N-1) of its egress to every peer and receives
+        # the same from each, so the switch is loaded evenly without a barrier per round (28 barriers of ~0.1 ms per
+        # step at N = 8 against pushes of 0.23 ms).  "rounds": the lock-step rotation described above.
+        import os
+        mode = os.environ.get("B200_EXCHANGE_MODE", "auto")
+        self.burst = mode == "burst" or (mode == "auto" and self.world >= 8)
+        self.peer_streams = [torch.cuda.Stream(priority=-1) for _ in range(self.world - 1)] if self.burst else []
         self.trace = None  # set to a list to collect (peer, row0, nbytes, start event, end event) per copy
         self.bytes_pushed = 0   # payload this rank sent since the counter was last reset (bench.py reports it)
 
@@ -237,18 +249,28 @@ class PeerImage:
         torch = self.torch
         lib = _lib.load()
         width = self.local.shape[-1]
-        st = self.fill_stream
-        st.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(st):
-            sp = int(st.cuda_stream)
+        key = (tuple(blocks), float(value) if value == value else "nan")
+        if getattr(self, "_rects_key", None) != key:      # the rectangle table of a fixed decomposition is built once
+            import ctypes as C
+            rects = []
             for row0, nrows, (c_lo, c_hi) in blocks:
                 if nrows <= 0:
                     continue
-                base = self.local[row0]
+                if c_hi <= c_lo:
+                    rects += [row0, nrows, 0, width]
+                    continue
                 if c_lo > 0:
-                    _lib.check(lib.b200_fill_f32_2d(base.data_ptr(), width, c_lo, nrows, value, sp))
+                    rects += [row0, nrows, 0, c_lo]
                 if c_hi < width:
-                    _lib.check(lib.b200_fill_f32_2d(base[c_hi:].data_ptr(), width, width - c_hi, nrows, value, sp))
+                    rects += [row0, nrows, c_hi, width - c_hi]
+            self._rects = (C.c_int64 * max(1, len(rects)))(*rects)
+            self._n_rects = len(rects) // 4
+            self._rects_key = key
+        st = self.fill_stream
+        st.wait_stream(torch.cuda.current_stream())
+        if self._n_rects:
+            _lib.check(lib.b200_fill_f32_rects(self.local.data_ptr(), width, self._rects, self._n_rects, value,
+                                               int(st.cuda_stream)))
 
     def push_rows(self, row0: int, nrows: int, after=None, col_span=None):
         """Copy rows [row0, row0 + nrows) of ``local`` into every peer's image (``nrows`` may be 0: the rank still
@@ -270,6 +292,22 @@ class PeerImage:
         empty = nrows <= 0 or c_hi <= c_lo
         nbytes = 0 if empty else nrows * (c_hi - c_lo) * esize
         lib = _lib.load()
+        if self.burst:
+            with torch.cuda.stream(st):
+                self.handle.barrier(channel=1, timeout_ms=self.BARRIER_TIMEOUT_MS)
+                start = torch.cuda.Event()
+                start.record(st)
+            if not empty:
+                for k in range(1, self.world):
+                    peer = round_peer(self.rank, k, self.world)
+                    ps = self.peer_streams[k - 1]
+                    ps.wait_event(start)
+                    _lib.check(lib.b200_copy_2d(self.peers[peer][row0, c_lo:].data_ptr(), width * esize,
+                                                mine[0, c_lo:].data_ptr(), width * esize, (c_hi - c_lo) * esize, nrows,
+                                                int(ps.cuda_stream)))
+                    self.bytes_pushed += nbytes
+                    st.wait_stream(ps)     # the next push (and finish) follow these copies
+            return
         with torch.cuda.stream(st):
             for k in range(1, self.world):
                 self.handle.barrier(channel=1, timeout_ms=self.BARRIER_TIMEOUT_MS)
