@@ -108,6 +108,13 @@ typedef struct b200_abi_cal {
 
 int b200_abi_calibrate(const int16_t *counts, float *out, int64_t n,
                        const b200_abi_cal_t *cal /* host */, void *stream);
+/* The same with the kernel variant chosen by the caller (benchmarks, tests): 0 = one 32-byte block per thread (first
+ * release), 1 = lane-interleaved 8-byte loads / 16-byte stores (every warp-level access one contiguous run),
+ * 2 = bulk-asynchronous staging through shared memory (cp.async.bulk + mbarrier in both directions: no thread issues
+ * a global load or store).  b200_abi_calibrate uses B200_CAL_VARIANT from the environment, else the measured winner.
+ * All variants give bit-identical results. */
+int b200_abi_calibrate_variant(const int16_t *counts, float *out, int64_t n, const b200_abi_cal_t *cal,
+                               int32_t variant, void *stream);
 
 /* AHI HSD (readers/ahi_hsd.py:607-611,675-750): uint16 counts -> radiance / reflectance [%] / BT [K].
  * The Planck constants are doubles; bt_in_f64 selects numpy's dtype flow when they are numpy float64
@@ -267,6 +274,13 @@ int b200_nn_query(const b200_nn_grid_t *grid, const b200_geo_t *dst, double radi
 int b200_nn_gather(const void *data, void *out, const int32_t *gather_index, int64_t n_out,
                    int32_t nbands, int64_t src_band_stride, int64_t dst_band_stride,
                    int32_t elem_size, const void *fill /* host */, void *stream);
+/* The same with the kernel variant chosen by the caller: 0 = direct (128-bit index loads and stores from the threads),
+ * 1 = index stream in and result out through shared memory with cp.async.bulk + mbarrier (4-byte elements, one band;
+ * anything else takes variant 0).  b200_nn_gather uses B200_GATHER_VARIANT from the environment, else the measured
+ * winner.  Both give identical results. */
+int b200_nn_gather_variant(const void *data, void *out, const int32_t *gather_index, int64_t n_out, int32_t nbands,
+                           int64_t src_band_stride, int64_t dst_band_stride, int32_t elem_size,
+                           const void *fill_value, int32_t variant, void *stream);
 
 /* Fused query + gather (no index materialised): float32 data only. */
 int b200_nn_query_gather_f32(const b200_nn_grid_t *grid, const b200_geo_t *dst, double radius,

@@ -85,6 +85,7 @@ SIGNATURES = {
     "b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "b200_area_lonlats": (C.c_int, [_GEO, _P, _P, _P]),
     "b200_abi_calibrate": (C.c_int, [_P, _P, C.c_int64, C.POINTER(AbiCalStruct), _P]),
+    "b200_abi_calibrate_variant": (C.c_int, [_P, _P, C.c_int64, C.POINTER(AbiCalStruct), C.c_int32, _P]),
     "b200_ahi_calibrate": (C.c_int, [_P, _P, C.c_int64, C.POINTER(AhiCalStruct), _P]),
     "b200_seviri_calibrate": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(SeviriCalStruct), _P]),
     "b200_viirs_scale": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_int32),
@@ -107,6 +108,7 @@ SIGNATURES = {
     "b200_nn_grid_nbytes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "b200_nn_query": (C.c_int, [_P, _GEO, C.c_double, _P, _P, _P, _P]),
     "b200_nn_gather": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
+    "b200_nn_gather_variant": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, _P]),
     "b200_nn_query_gather_f32": (C.c_int, [_P, _GEO, C.c_double, _P, _P, C.c_int32, C.c_int64, C.c_int64,
                                            C.c_float, _P]),
     "b200_nn_compressed_to_raw": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P]),

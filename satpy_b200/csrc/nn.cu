@@ -23,9 +23,11 @@
 // Targets whose lon depends on the column only and lat on the row only (longlat / eqc / merc) get
 // per-column and per-row tables so that no transcendental is evaluated per pixel.
 #include <climits>
+#include <stdlib.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include "nn_common.cuh"
+#include "b200_bulk.cuh"
 #include "b200_geos_fast.cuh"
 
 #define B200_NN_MAX_CELLS (160LL * 1000 * 1000)
@@ -825,12 +827,101 @@ static void launch_gather(const void *data, void *out, const int32_t *gidx, int6
                                                                    src_band_stride, dst_band_stride, f);
 }
 
+// Bulk-staged variant (float32 / 4-byte elements, one band): the index stream comes in and the result goes out through
+// shared memory with cp.async.bulk (b200_bulk.cuh), GATHER_STAGES tiles in flight per CTA; threads only issue the
+// scattered source loads.  A/B against the direct kernel in scripts/variant_bench.py.
+#define GATHER_TILE 2048
+#define GATHER_STAGES 3
+struct __align__(128) GatherStage {
+    int32_t idx[GATHER_TILE];
+    uint32_t out[GATHER_TILE];
+};
+
+__global__ void __launch_bounds__(256)
+nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ out, const int32_t *__restrict__ gidx,
+                      int64_t n_tiles, uint32_t fill) {
+    extern __shared__ __align__(128) unsigned char gather_smem[];
+    GatherStage *stage = reinterpret_cast<GatherStage *>(gather_smem);
+    __shared__ uint64_t full[GATHER_STAGES];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < GATHER_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    if (t == 0) {
+        for (int s = 0; s < GATHER_STAGES; ++s) {
+            const int64_t tile = first + (int64_t)s * step;
+            if (tile < n_tiles) {
+                mbar_expect_tx(&full[s], GATHER_TILE * 4);
+                bulk_g2s(stage[s].idx, gidx + tile * GATHER_TILE, GATHER_TILE * 4, &full[s]);
+            }
+        }
+    }
+    int s = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += step) {
+        mbar_wait(&full[s], phase);
+        if (t == 0) bulk_wait_read<GATHER_STAGES - 1>();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < GATHER_TILE / 1024; ++j) {
+            const int4 ix = *reinterpret_cast<const int4 *>(stage[s].idx + j * 1024 + 4 * t);
+            uint4 v;
+            v.x = ix.x < 0 ? fill : __ldg(data + ix.x);
+            v.y = ix.y < 0 ? fill : __ldg(data + ix.y);
+            v.z = ix.z < 0 ? fill : __ldg(data + ix.z);
+            v.w = ix.w < 0 ? fill : __ldg(data + ix.w);
+            *reinterpret_cast<uint4 *>(stage[s].out + j * 1024 + 4 * t) = v;
+        }
+        bulk_fence_smem_writes();
+        __syncthreads();
+        if (t == 0) {
+            bulk_s2g(out + tile * GATHER_TILE, stage[s].out, GATHER_TILE * 4);
+            bulk_commit();
+            const int64_t next = tile + (int64_t)GATHER_STAGES * step;
+            if (next < n_tiles) {
+                mbar_expect_tx(&full[s], GATHER_TILE * 4);
+                bulk_g2s(stage[s].idx, gidx + next * GATHER_TILE, GATHER_TILE * 4, &full[s]);
+            }
+        }
+        if (++s == GATHER_STAGES) {
+            s = 0;
+            phase ^= 1;
+        }
+    }
+    if (t == 0) bulk_wait_all();
+}
+
+static int g_gather_variant = -1;
+#ifndef B200_GATHER_DEFAULT_VARIANT
+#define B200_GATHER_DEFAULT_VARIANT 0
+#endif
+
+extern "C" int b200_nn_gather_variant(const void *data, void *out, const int32_t *gather_index, int64_t n_out,
+                                      int32_t nbands, int64_t src_band_stride, int64_t dst_band_stride,
+                                      int32_t elem_size, const void *fill_value, int32_t variant, void *stream);
+
 extern "C" int b200_nn_gather(const void *data, void *out, const int32_t *gather_index, int64_t n_out, int32_t nbands,
                               int64_t src_band_stride, int64_t dst_band_stride, int32_t elem_size, const void *fill,
                               void *stream) {
+    if (g_gather_variant < 0) {
+        const char *e = getenv("B200_GATHER_VARIANT");
+        g_gather_variant = e ? atoi(e) : B200_GATHER_DEFAULT_VARIANT;
+        if (g_gather_variant < 0 || g_gather_variant > 1) g_gather_variant = B200_GATHER_DEFAULT_VARIANT;
+    }
+    return b200_nn_gather_variant(data, out, gather_index, n_out, nbands, src_band_stride, dst_band_stride, elem_size,
+                                  fill, g_gather_variant, stream);
+}
+
+extern "C" int b200_nn_gather_variant(const void *data, void *out, const int32_t *gather_index, int64_t n_out,
+                                      int32_t nbands, int64_t src_band_stride, int64_t dst_band_stride,
+                                      int32_t elem_size, const void *fill, int32_t variant, void *stream) {
     B200_CHECK_ARG(n_out >= 0 && nbands >= 1, "bad shape");
     B200_CHECK_ARG(elem_size == 1 || elem_size == 2 || elem_size == 4 || elem_size == 8,
                    "elem_size must be 1, 2, 4 or 8");
+    B200_CHECK_ARG(variant == 0 || variant == 1, "variant must be 0 (direct) or 1 (bulk-staged)");
     B200_CHECK_ARG(fill != nullptr, "fill is NULL");
     if (n_out == 0) return B200_OK;
     B200_CHECK_ARG(data != nullptr && out != nullptr && gather_index != nullptr, "NULL data pointer");
@@ -839,11 +930,34 @@ extern "C" int b200_nn_gather(const void *data, void *out, const int32_t *gather
                    "data and out must be aligned to the element size");
     B200_CHECK_ARG(nbands == 1 || dst_band_stride >= n_out, "band stride smaller than one image");
     cudaStream_t s = (cudaStream_t)stream;
+    int64_t done = 0;
+    if (variant == 1 && elem_size == 4 && nbands == 1 && (((uintptr_t)out) & 15) == 0 && n_out >= GATHER_TILE) {
+        // whole tiles through the bulk-staged kernel, the rest (< one tile) through the direct one
+        const int64_t n_tiles = n_out / GATHER_TILE;
+        const size_t smem = sizeof(GatherStage) * GATHER_STAGES + 128;
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200_CUDA(cudaFuncSetAttribute(nn_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        int64_t grid = (int64_t)B200_NUM_SMS * 4;
+        if (grid > n_tiles) grid = n_tiles;
+        uint32_t f;
+        memcpy(&f, fill, 4);
+        nn_gather_bulk_kernel<<<(int)grid, 256, smem, s>>>(static_cast<const uint32_t *>(data), static_cast<uint32_t *>(out),
+                                                         gather_index, n_tiles, f);
+        B200_LAUNCH_CHECK();
+        done = n_tiles * GATHER_TILE;
+        if (done == n_out) return B200_OK;
+    }
+    const char *o = static_cast<char *>(out) + done * elem_size;
+    const int32_t *gi = gather_index + done;
+    const int64_t n = n_out - done;
     switch (elem_size) {
-    case 1: launch_gather<uint8_t>(data, out, gather_index, n_out, nbands, src_band_stride, dst_band_stride, fill, s); break;
-    case 2: launch_gather<uint16_t>(data, out, gather_index, n_out, nbands, src_band_stride, dst_band_stride, fill, s); break;
-    case 4: launch_gather<uint32_t>(data, out, gather_index, n_out, nbands, src_band_stride, dst_band_stride, fill, s); break;
-    default: launch_gather<uint64_t>(data, out, gather_index, n_out, nbands, src_band_stride, dst_band_stride, fill, s); break;
+    case 1: launch_gather<uint8_t>(data, (void *)o, gi, n, nbands, src_band_stride, dst_band_stride, fill, s); break;
+    case 2: launch_gather<uint16_t>(data, (void *)o, gi, n, nbands, src_band_stride, dst_band_stride, fill, s); break;
+    case 4: launch_gather<uint32_t>(data, (void *)o, gi, n, nbands, src_band_stride, dst_band_stride, fill, s); break;
+    default: launch_gather<uint64_t>(data, (void *)o, gi, n, nbands, src_band_stride, dst_band_stride, fill, s); break;
     }
     B200_LAUNCH_CHECK();
     return B200_OK;

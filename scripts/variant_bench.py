@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""A/B of the kernel variants that exist for north_star's "coalesced 128-bit access / TMA row staging" question:
+ABI calibration (0 = per-thread blocks, 1 = lane-interleaved, 2 = cp.async.bulk staging) and the cached-index
+gather (0 = direct, 1 = bulk-staged index and output streams), at the config-5 sizes, CUDA events, 20 launches each.
+
+    python scripts/variant_bench.py [--out profiles/r02_variant_bench.json]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from satpy_b200 import _lib, demo  # noqa: E402
+
+
+def timeit(fn, steps=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    lib = _lib.load()
+    try:
+        pk = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pk = 6554.9
+    rows = []
+    src = demo.make_area("goes_east_abi_f_1km")
+    n = src.size
+    counts = torch.from_numpy(demo.abi_counts(src.shape, 7, "C02")).cuda()
+    out = torch.empty(src.shape, dtype=torch.float32, device="cuda")
+    ref = {}
+    stream = _lib.stream_ptr(torch)
+    for band, calib in (("C02", "radiance"), ("C02", "reflectance"), ("C13", "brightness_temperature")):
+        st = demo.abi_calibration(band).struct(calib)
+        for variant in (0, 1, 2):
+            def run():
+                _lib.check(lib.b200_abi_calibrate_variant(counts.data_ptr(), out.data_ptr(), n, C.byref(st), variant, stream))
+            ms = timeit(run)
+            same = None
+            if variant == 0:
+                ref[calib] = out.clone()
+            else:
+                same = bool(((out == ref[calib]) | (torch.isnan(out) & torch.isnan(ref[calib]))).all())
+            r = {"kernel": "abi_calibrate", "variant": variant, "mode": calib, "ms": round(ms, 4),
+                 "gbs": round(6 * n / ms / 1e6, 1), "frac_of_measured_hbm": round(6 * n / ms / 1e6 / pk, 3),
+                 "identical_to_variant_0": same}
+            rows.append(r)
+            print(json.dumps(r), flush=True)
+    if hasattr(lib, "b200_nn_gather_variant"):
+        from satpy_b200.resample import B200NearestResampler
+        dst = demo.make_area("global_eqc_500m")
+        r = B200NearestResampler(src, dst)
+        r.precompute(radius_of_influence=2000.0, gather_only=True)
+        gi = r._current["gather_index"]
+        data = torch.rand(src.shape, device="cuda")
+        res = torch.empty(dst.shape, dtype=torch.float32, device="cuda")
+        fill = (C.c_char * 4).from_buffer_copy(np.float32(np.nan).tobytes())
+        n_valid = int(np.pi / 4 * n)
+        first = None
+        for variant in (0, 1):
+            def run():
+                _lib.check(lib.b200_nn_gather_variant(data.data_ptr(), res.data_ptr(), gi.data_ptr(), gi.numel(), 1, n,
+                                                      gi.numel(), 4, C.cast(fill, C.c_void_p), variant, stream))
+            ms = timeit(run, steps=5)
+            same = None
+            if variant == 0:
+                first = res.clone()
+            else:
+                same = bool(((res == first) | (torch.isnan(res) & torch.isnan(first))).all())
+            nbytes = 8 * dst.size + 4 * n_valid
+            rr = {"kernel": "nn_gather", "variant": variant, "ms": round(ms, 4), "gbs": round(nbytes / ms / 1e6, 1),
+                  "frac_of_measured_hbm": round(nbytes / ms / 1e6 / pk, 3), "identical_to_variant_0": same}
+            rows.append(rr)
+            print(json.dumps(rr), flush=True)
+    if args.out:
+        json.dump(rows, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,3 +88,36 @@ def test_span_exchange_reassembles_the_image_on_every_rank(world, nsub):
         for b, (r0, n) in enumerate(blocks):
             np.testing.assert_array_equal(got[b * block_rows: b * block_rows + n], ref[r0:r0 + n],
                                           err_msg=f"rank {rank}, block {b}")
+
+
+@pytest.mark.parametrize("n", [5, 4096, 3 * 4096 + 1234, 1 << 20])
+def test_calibration_and_gather_variants_are_bit_identical(n):
+    """The lane-interleaved and the bulk-asynchronous (cp.async.bulk + mbarrier) kernels against the first release's,
+    on sizes with ragged tails (less than one tile, whole tiles + a tail)."""
+    import torch
+    lib = _lib.load()
+    stream = _lib.stream_ptr(torch)
+    rng = np.random.default_rng(n)
+    counts = torch.from_numpy(rng.integers(0, 4096, size=n).astype(np.int16)).cuda()
+    for band, calib in (("C02", "radiance"), ("C02", "reflectance"), ("C13", "brightness_temperature")):
+        st = demo.abi_calibration(band).struct(calib)
+        outs = []
+        for variant in (0, 1, 2):
+            out = torch.full((n,), -3.0, dtype=torch.float32, device="cuda")
+            _lib.check(lib.b200_abi_calibrate_variant(counts.data_ptr(), out.data_ptr(), n, C.byref(st), variant, stream))
+            outs.append(out.cpu().numpy())
+        np.testing.assert_array_equal(outs[1], outs[0])
+        np.testing.assert_array_equal(outs[2], outs[0])
+    n_src = 50000
+    data = torch.from_numpy(rng.uniform(0, 100, size=n_src).astype(np.float32)).cuda()
+    gi = torch.from_numpy(rng.integers(-1, n_src, size=n).astype(np.int32)).cuda()
+    fill = (C.c_char * 4).from_buffer_copy(np.float32(np.nan).tobytes())
+    res = []
+    for variant in (0, 1):
+        out = torch.full((n,), -3.0, dtype=torch.float32, device="cuda")
+        _lib.check(lib.b200_nn_gather_variant(data.data_ptr(), out.data_ptr(), gi.data_ptr(), n, 1, n_src, n, 4,
+                                              C.cast(fill, C.c_void_p), variant, stream))
+        res.append(out.cpu().numpy())
+    np.testing.assert_array_equal(res[1], res[0])
+    exp = np.where(gi.cpu().numpy() < 0, np.nan, data.cpu().numpy()[np.maximum(gi.cpu().numpy(), 0)])
+    np.testing.assert_array_equal(res[0], exp.astype(np.float32))
