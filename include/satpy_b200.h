@@ -209,6 +209,11 @@ int b200_relative_azimuth(const void *sat_azi, const void *sun_azi, void *out, i
 /* SunZenithReducer (modifiers/geometry.py:166-207 -> angles.py:594-624): out = data * reduction(sza). */
 int b200_sunz_reduce(const float *data, const float *sunz_deg, float *out, int32_t nbands, int64_t band_stride,
                      int64_t n, float limit_deg, float max_sza_deg, float strength, void *stream);
+/* SunZenithReducer when no solar-zenith dataset is given (geometry.py:166-207): the angle is derived from the area in
+ * the same launch -- cos(sza) in the reference's flow (b200_cos_sza), masked beyond sz->max_sza_deg (geometry.py:62-63),
+ * sza = rad2deg(arccos(.)) rounded to float32 (geometry.py:201), then b200_sunz_reduce's factor. */
+int b200_sunz_reduce_area(const float *data, float *out, int32_t nbands, int64_t band_stride, const b200_geo_t *geo,
+                          const b200_sunz_t *sz, float limit_deg, float max_sza_deg, float strength, void *stream);
 
 /* Fused reader calibration + SunZenithCorrector for up to 4 ABI reflective bands
  * sharing one area: counts -> radiance -> reflectance[%] -> * corr.  6 B/pixel/band. */
@@ -302,6 +307,21 @@ int b200_native_aggregate_f32(const float *data, float *out, int64_t out_rows, i
                               int32_t fx, void *stream);
 int b200_simulated_green(const float *c01, const float *c02, const float *c03, float *out, int64_t n, float f1,
                          float f2, float f3, void *stream);
+
+/* RatioSharpenedRGB / SelfSharpenedRGB (composites/resolution.py:32-233) with GenericCompositor's common channel
+ * mask (composites/core.py:489-490): out (3 x H x W) from three bands of one shape.
+ *   high        the high-resolution band (NULL: stack + mask only, "high_resolution_band: None")
+ *   hi          colour (0 red, 1 green, 2 blue) `high` stands for; out[hi] = high
+ *   neutral     colour left untouched (-1: none)
+ *   self_mean   1: ratio = high / four_element_average(high) (SelfSharpenedRGB, _mean4 :168-192, blocks anchored at
+ *               the parities row_off / col_off of the area's crop offset); 0: ratio = high / band[hi]
+ *   ratio       1 where not finite or negative, clipped to 1.5 (:157-165) */
+int b200_ratio_sharpen_f32(const float *red, const float *green, const float *blue, const float *high, float *out,
+                           int64_t H, int64_t W, int32_t hi, int32_t neutral, int32_t self_mean, int32_t row_off,
+                           int32_t col_off, int32_t common_mask, void *stream);
+int b200_ratio_sharpen_f64(const double *red, const double *green, const double *blue, const double *high, double *out,
+                           int64_t H, int64_t W, int32_t hi, int32_t neutral, int32_t self_mean, int32_t row_off,
+                           int32_t col_off, int32_t common_mask, void *stream);
 
 /* ---------------------------------------------------------------- assembling a row-tiled image
  * Multi-GPU decomposition of the target (the reference's analogue is dask chunking of the

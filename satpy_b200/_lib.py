@@ -93,6 +93,8 @@ SIGNATURES = {
     "b200_get_angles": (C.c_int, [_GEO, C.POINTER(SunzStruct), C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P]),
     "b200_relative_azimuth": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
     "b200_sunz_reduce": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, _P]),
+    "b200_sunz_reduce_area": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _GEO, C.POINTER(SunzStruct), C.c_float, C.c_float,
+                                        C.c_float, _P]),
     "b200_cos_sza": (C.c_int, [_GEO, C.POINTER(SunzStruct), _P, _P]),
     "b200_sunz_correct": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _GEO, C.POINTER(SunzStruct), _P]),
     "b200_sunz_correct_f64": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _GEO, C.POINTER(SunzStruct), _P]),
@@ -115,6 +117,10 @@ SIGNATURES = {
     "b200_native_replicate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "b200_native_aggregate_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
     "b200_simulated_green": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _P]),
+    "b200_ratio_sharpen_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, _P]),
+    "b200_ratio_sharpen_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, _P]),
     "b200_fill_f32_2d": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_float, _P]),
     "b200_fill_f32_rects": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), C.c_int32, C.c_float, _P]),
     "b200_copy_2d": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, _P]),

@@ -8,6 +8,7 @@
 // satpy/tests/reader_tests/test_ahi_hsd.py:455-506, test_seviri_l1b_calibration.py:29-149.
 #include <new>
 #include "b200_common.cuh"
+#include "b200_reduce.cuh"
 
 #define NANF __int_as_float(0x7fc00000)
 
@@ -200,15 +201,7 @@ sunz_reduce_kernel(const float *__restrict__ data, const float *__restrict__ sun
                    int nbands, int64_t band_stride, float limit, float max_sza, float strength) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float z = sunz[i];
-        float rf = __fdiv_rn(__fsub_rn(z, limit), __fsub_rn(max_sza, limit));
-        rf = fminf(fmaxf(rf, 0.0f), 1.0f);
-        if (isnan(z)) rf = NANF;  // clip keeps NaN
-        rf = __fsub_rn(1.0f, log2f(__fadd_rn(rf, 1.0f)));
-        const float p = powf(rf, strength), q = powf(__fsub_rn(1.0f, rf), strength);
-        rf = __fdiv_rn(p, __fadd_rn(p, q));
-        float corr = z < limit ? 1.0f : rf;
-        if (isnan(z)) corr = 0.0f;
+        const float corr = b200_sunz_reduction(sunz[i], limit, max_sza, strength);
         for (int b = 0; b < nbands; ++b) st_stream_f1(out + b * band_stride + i, __fmul_rn(data[b * band_stride + i], corr));
     }
 }

@@ -93,3 +93,112 @@ extern "C" int b200_simulated_green(const float *c01, const float *c02, const fl
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RatioSharpenedRGB / SelfSharpenedRGB (satpy/composites/resolution.py:32-233) + the common channel mask of
+// GenericCompositor (satpy/composites/core.py:489-490) in one pass:
+//   ratio = high / low;  ratio = 1 where it is not finite or negative;  ratio = min(ratio, 1.5)       (:157-165)
+//   out[hi] = high;  out[c] = band[c] * ratio for the other colours except the neutral one           (:143-154)
+//   SelfSharpenedRGB: low = four_element_average(high): nanmean over 2 x 2 blocks anchored at the crop offset's
+//   parity, edge-padded, repeated back to full resolution (_mean4, :168-192)
+//   common mask: a pixel that is NaN in any of the three bands is NaN in all of them.
+// One thread = one 2 x 2 block (the four pixels share the mean): two 8-byte accesses per band and row.
+template <typename T>
+struct SharpenArg {
+    const T *band[3];
+    const T *high;   // the high-resolution band (NULL: no sharpening, the bands are only stacked and masked)
+    T *out;          // 3 x H x W
+    int64_t H, W;
+    int32_t hi, neutral, self_mean, row_off, col_off, common_mask;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) ratio_sharpen_kernel(const __grid_constant__ SharpenArg<T> A) {
+    const int64_t bw = (A.W + A.col_off + 1) / 2, bh = (A.H + A.row_off + 1) / 2;
+    const int64_t n = bw * bh;
+    const T nan = (T)__int_as_float(0x7fc00000);
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t bi = i / bw, bj = i - bi * bw;
+        const int64_t r0 = 2 * bi - A.row_off, c0 = 2 * bj - A.col_off;
+        // four-element average of the block's in-image pixels (edge padding repeats them: the mean is the same)
+        T mean = nan;
+        if (A.high && A.self_mean) {
+            T sum = 0;
+            int cnt = 0;
+#pragma unroll
+            for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+                for (int dc = 0; dc < 2; ++dc) {
+                    const int64_t r = r0 + dr, c = c0 + dc;
+                    if (r < 0 || r >= A.H || c < 0 || c >= A.W) continue;
+                    const T v = A.high[r * A.W + c];
+                    if (v == v) {
+                        sum += v;
+                        ++cnt;
+                    }
+                }
+            if (cnt) mean = sum / (T)cnt;
+        }
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+            for (int dc = 0; dc < 2; ++dc) {
+                const int64_t r = r0 + dr, c = c0 + dc;
+                if (r < 0 || r >= A.H || c < 0 || c >= A.W) continue;
+                const int64_t p = r * A.W + c;
+                T v[3] = {A.band[0][p], A.band[1][p], A.band[2][p]};
+                if (A.high) {
+                    const T h = A.high[p];
+                    const T low = A.self_mean ? mean : v[A.hi];
+                    T ratio = h / low;
+                    const bool finite = sizeof(T) == 4 ? (fabsf((float)ratio) <= 3.4028235e38f)
+                                                       : (fabs((double)ratio) <= 1.7976931348623157e308);   // NaN fails too
+                    if (!finite || ratio < (T)0) ratio = (T)1;
+                    ratio = ratio > (T)1.5 ? (T)1.5 : ratio;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (k == A.hi) v[k] = h;
+                        else if (k != A.neutral) v[k] = v[k] * ratio;
+                    }
+                }
+                if (A.common_mask && (v[0] != v[0] || v[1] != v[1] || v[2] != v[2])) v[0] = v[1] = v[2] = nan;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) A.out[k * A.H * A.W + p] = v[k];
+            }
+    }
+}
+
+template <typename T>
+static int ratio_sharpen(const T *red, const T *green, const T *blue, const T *high, T *out, int64_t H, int64_t W,
+                         int32_t hi, int32_t neutral, int32_t self_mean, int32_t row_off, int32_t col_off,
+                         int32_t common_mask, void *stream) {
+    B200_CHECK_ARG(H >= 0 && W >= 0, "bad shape");
+    B200_CHECK_ARG(hi >= 0 && hi <= 2 && neutral >= -1 && neutral <= 2, "colour index outside 0..2");
+    B200_CHECK_ARG((row_off == 0 || row_off == 1) && (col_off == 0 || col_off == 1), "offsets are parities (0 or 1)");
+    if (H * W == 0) return B200_OK;
+    B200_CHECK_ARG(red && green && blue && out, "NULL data pointer");
+    SharpenArg<T> A;
+    A.band[0] = red, A.band[1] = green, A.band[2] = blue;
+    A.high = high;
+    A.out = out;
+    A.H = H, A.W = W;
+    A.hi = hi, A.neutral = neutral, A.self_mean = self_mean, A.row_off = row_off, A.col_off = col_off;
+    A.common_mask = common_mask;
+    const int64_t blocks = ((W + col_off + 1) / 2) * ((H + row_off + 1) / 2);
+    ratio_sharpen_kernel<T><<<b200_grid_for(blocks, 256, 8), 256, 0, (cudaStream_t)stream>>>(A);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_ratio_sharpen_f32(const float *red, const float *green, const float *blue, const float *high,
+                                      float *out, int64_t H, int64_t W, int32_t hi, int32_t neutral, int32_t self_mean,
+                                      int32_t row_off, int32_t col_off, int32_t common_mask, void *stream) {
+    return ratio_sharpen<float>(red, green, blue, high, out, H, W, hi, neutral, self_mean, row_off, col_off, common_mask, stream);
+}
+
+extern "C" int b200_ratio_sharpen_f64(const double *red, const double *green, const double *blue, const double *high,
+                                      double *out, int64_t H, int64_t W, int32_t hi, int32_t neutral, int32_t self_mean,
+                                      int32_t row_off, int32_t col_off, int32_t common_mask, void *stream) {
+    return ratio_sharpen<double>(red, green, blue, high, out, H, W, hi, neutral, self_mean, row_off, col_off, common_mask, stream);
+}

@@ -896,7 +896,7 @@ nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ 
 
 static int g_gather_variant = -1;
 #ifndef B200_GATHER_DEFAULT_VARIANT
-#define B200_GATHER_DEFAULT_VARIANT 0
+#define B200_GATHER_DEFAULT_VARIANT 1
 #endif
 
 extern "C" int b200_nn_gather_variant(const void *data, void *out, const int32_t *gather_index, int64_t n_out,

@@ -16,6 +16,7 @@
 #include "b200_proj.cuh"
 #include "b200_cal.cuh"
 #include "b200_geos_fast.cuh"
+#include "b200_reduce.cuh"
 
 #define B200_DEG2RAD_F 0.017453292f  // numpy's float32 deg2rad factor
 
@@ -616,6 +617,51 @@ extern "C" int b200_sunz_correct_sza(const float *data, const float *sza_deg, fl
     B200_CHECK_ARG(nbands == 1 || band_stride >= n, "band stride smaller than one image");
     sunz_correct_sza_kernel<<<b200_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         data, sza_deg, out, nbands, band_stride, n, S);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// SunZenithReducer without a solar-zenith dataset (satpy/modifiers/geometry.py:166-207): cos(sza) of the area in the
+// reference's flow, masked beyond max_sza (geometry.py:62-63), sza = rad2deg(arccos(.)) (geometry.py:201) rounded to the
+// data's float32, then the reduction factor -- one launch instead of a cos(sza) image and three element-wise passes.
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+sunz_reduce_area_kernel(const float *__restrict__ data, float *__restrict__ out, int nbands, int64_t band_stride,
+                        float limit, float max_sza, float strength, const __grid_constant__ SunzDev S) {
+    const int W = (int)S.geo.width;
+    const int64_t nrows = S.geo.nrows;
+    for (int64_t r = blockIdx.y; r < nrows; r += gridDim.y) {
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < W; c += gridDim.x * blockDim.x) {
+            double cz = b200_cos_sza_pixel<false, FAST>(S, S.geo.row0 + r, c);
+            if (S.has_max && !(cz >= S.max_cos)) cz = __longlong_as_double(0x7ff8000000000000LL);
+            const float z = (float)(acos(cz) * 57.29577951308232);
+            const float corr = b200_sunz_reduction(z, limit, max_sza, strength);
+            const int64_t i = r * W + c;
+            for (int b = 0; b < nbands; ++b) out[b * band_stride + i] = __fmul_rn(data[b * band_stride + i], corr);
+        }
+    }
+}
+
+extern "C" int b200_sunz_reduce_area(const float *data, float *out, int32_t nbands, int64_t band_stride,
+                                     const b200_geo_t *geo, const b200_sunz_t *sz, float limit_deg, float max_sza_deg,
+                                     float strength, void *stream) {
+    SunzDev S;
+    int rc = fill_sunz(S, geo, sz, true);
+    if (rc) return rc;
+    B200_CHECK_ARG(nbands >= 1, "nbands must be >= 1");
+    B200_CHECK_ARG(geo->width < (1LL << 31), "area too wide");
+    int64_t n = geo->nrows * geo->width;
+    if (n == 0) return B200_OK;
+    B200_CHECK_ARG(data != nullptr && out != nullptr, "NULL data pointer");
+    B200_CHECK_ARG(nbands == 1 || band_stride >= n, "band stride smaller than one image");
+    rc = b200_geos_fast_prepare(geo, &S.fast, (cudaStream_t)stream);
+    if (rc) return rc;
+    const dim3 grid((unsigned)((geo->width + 255) / 256), (unsigned)(geo->nrows < 8192 ? geo->nrows : 8192));
+    if (S.fast.enabled)
+        sunz_reduce_area_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, limit_deg, max_sza_deg, strength, S);
+    else
+        sunz_reduce_area_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(data, out, nbands, band_stride, limit_deg, max_sza_deg, strength, S);
+    b200_geos_fast_release(&S.fast, (cudaStream_t)stream);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -225,14 +225,28 @@ class SunZenithReducer(_SunZenithCorrectorBase):
             return vis
         torch = _lib.require_cuda()
         if len(arrays) < 2:
-            cz = cos_sza(vis.attrs["area"], vis.attrs["start_time"], lonlat_f32=True, device=True)
-            cz = torch.where(cz >= float(self.max_sza_cos), cz, torch.full_like(cz, float("nan")))
+            # angle derived from the area inside the kernel (cos(sza) -> mask -> arccos -> degrees -> factor)
+            t, was_numpy = _to_cuda_f32(torch, payload(vis))
+            area = as_geometry(vis.attrs["area"])
+            if t.dim() not in (2, 3) or tuple(t.shape[-2:]) != area.shape:
+                raise IncompatibleAreas(f"data shape {tuple(t.shape)} does not fit area shape {area.shape}")
+            nbands = 1 if t.dim() == 2 else t.shape[0]
+            out = torch.empty_like(t)
+            g = area.geo_struct()
+            s = _sunz_struct(vis.attrs["start_time"], self.correction_limit, self.max_sza, True, 0)
+            _lib.check(_lib.load().b200_sunz_reduce_area(t.data_ptr(), out.data_ptr(), nbands, area.size, C.byref(g),
+                                                         C.byref(s), float(self.correction_limit), float(self.max_sza),
+                                                         float(self.strength), _lib.stream_ptr(torch)))
+            res = _xfer.to_host(out) if was_numpy else out
         else:
+            # the solar zenith angle is a dataset: the reference goes through cos() and back (geometry.py:64-66,201);
+            # that round trip stays in PyTorch (a rarely used branch), the reduction itself is the kernel
             z = payload(arrays[1])
             z = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z))
             cz = torch.cos(torch.deg2rad(z.to("cuda")))
-        sunz = torch.rad2deg(torch.arccos(cz)).to(torch.float32)   # geometry.py:201
-        res = sunz_reduce(payload(vis), sunz, limit=self.correction_limit, max_sza=self.max_sza, strength=self.strength)
+            sunz = torch.rad2deg(torch.arccos(cz)).to(torch.float32)
+            res = sunz_reduce(payload(vis), sunz, limit=self.correction_limit, max_sza=self.max_sza,
+                              strength=self.strength)
         proj = rewrap(vis, res, attrs=dict(vis.attrs))
         self.apply_modifier_info(vis, proj)
         return proj

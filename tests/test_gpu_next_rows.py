@@ -245,3 +245,69 @@ def test_get_angles_matches_oracle_and_relative_azimuth_golden():
         assert raa.dtype == dtype
         np.testing.assert_allclose(np.array([180., 17.7, 175.06, 54.78, 98.8, 0.], dtype=dtype), raa, rtol=2e-7)
         np.testing.assert_array_equal(raa, osolar.compute_relative_azimuth(vaa, saa))
+
+
+# ------------------------------------------------------------------------------- ratio sharpening
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_ratio_and_self_sharpened_rgb_golden_and_oracle(dtype):
+    """RatioSharpenedRGB / SelfSharpenedRGB: the reference's golden vectors (satpy/tests/compositor_tests/
+    test_resolution.py:143-215), error behaviour (:96-121), then odd shapes, crop offsets and NaNs vs the oracle."""
+    from oracle import composites as oc
+    from satpy_b200 import DataArrayLite
+    from satpy_b200.composites import RatioSharpenedRGB, SelfSharpenedRGB
+    from satpy_b200.modifiers import IncompatibleAreas
+    from tests.test_oracle_golden import SHARPEN_CASES, _sharpen_fixture
+    low, ds2, ds3, high = _sharpen_fixture(dtype)
+    attrs = {"resolution": 1000, "calibration": "reflectance", "units": "%", "name": "test_vis"}
+    mk = lambda a, **kw: DataArrayLite(a, ("y", "x"), dict(attrs, **kw))   # noqa: E731
+    for hi, neutral, exp_r, exp_g, exp_b in SHARPEN_CASES:
+        comp = RatioSharpenedRGB(name="true_color", high_resolution_band=hi, neutral_resolution_band=neutral)
+        res = comp((mk(low), mk(ds2), mk(ds3)), optional_datasets=(mk(high, resolution=500),))
+        assert "units" not in res.attrs and res.attrs["name"] == "true_color" and res.attrs["resolution"] == 500
+        assert res.dims == ("bands", "y", "x") and list(res.coords["bands"]) == ["R", "G", "B"]
+        data = res.values
+        assert data.dtype == dtype and data.shape == (3, 2, 2)
+        for got, exp in zip(data, (exp_r, exp_g, exp_b)):
+            np.testing.assert_allclose(got, np.array(exp), rtol=1e-5)
+    data = SelfSharpenedRGB(name="true_color")((mk(low), mk(ds2), mk(ds3))).values
+    np.testing.assert_allclose(data[0], [[5.0, 5.0], [5.0, 0]], rtol=1e-5)
+    np.testing.assert_allclose(data[1], [[4.0, 4.0], [4.0, 0]], rtol=1e-5)
+    np.testing.assert_allclose(data[2], [[16 / 3, 16 / 3], [16 / 3, 0]], rtol=1e-5)
+    res = RatioSharpenedRGB(name="true_color", high_resolution_band=None)((mk(low), mk(ds2), mk(ds3)),
+                                                                            optional_datasets=(mk(high),))
+    assert res.values.shape == (3, 2, 2) and res.values.dtype == dtype
+    with pytest.raises(ValueError):
+        RatioSharpenedRGB(name="x", high_resolution_band="bad")
+    with pytest.raises(ValueError):
+        RatioSharpenedRGB(name="x")((mk(low), mk(ds2), mk(ds3), mk(ds3)))
+    with pytest.raises(IncompatibleAreas):
+        RatioSharpenedRGB(name="x")((mk(low), mk(ds2), mk(ds3)), optional_datasets=(mk(np.ones((4, 4), dtype)),))
+    with pytest.raises(ValueError, match="at least one high resolution band"):
+        SelfSharpenedRGB(name="x", high_resolution_band=None)((mk(low), mk(ds2), mk(ds3)))
+    # bigger, odd-shaped, with NaNs and both crop-offset parities
+    rng = np.random.default_rng(11)
+    shape = (301, 413)
+    bands = [rng.uniform(0, 100, size=shape).astype(dtype) for _ in range(3)]
+    bands[0][rng.random(shape) < 0.02] = np.nan
+    bands[1][rng.random(shape) < 0.01] = np.nan
+    bands[0][rng.random(shape) < 0.01] = 0.0
+    hi_band = rng.uniform(0, 100, size=shape).astype(dtype)
+    hi_band[rng.random(shape) < 0.02] = np.nan
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    for hi, neutral in (("red", None), ("green", "blue")):
+        got = RatioSharpenedRGB(name="t", high_resolution_band=hi, neutral_resolution_band=neutral)(
+            bands, optional_datasets=(hi_band,))
+        exp = oc.ratio_sharpened_rgb(*bands, hi_band, hi, neutral)
+        np.testing.assert_allclose(got, exp, rtol=tol, equal_nan=True)
+
+    class _Area:
+        def __init__(self, off):
+            self.crop_offset = off
+    for off in ((0, 0), (1, 0), (0, 1), (3, 5)):
+        ds = [DataArrayLite(b, ("y", "x"), {"area": _Area(off)}) for b in bands]
+        got = SelfSharpenedRGB(name="t", high_resolution_band="red")(ds).values
+        exp = oc.ratio_sharpened_rgb(*bands, None, "red", None, self_sharpen=True, offset=off)
+        np.testing.assert_allclose(got, exp, rtol=tol, equal_nan=True)
+    unmasked = SelfSharpenedRGB(name="t", common_channel_mask=False)(bands)
+    exp = oc.ratio_sharpened_rgb(*bands, None, "red", None, self_sharpen=True, common_channel_mask=False)
+    np.testing.assert_allclose(unmasked, exp, rtol=tol, equal_nan=True)

@@ -407,3 +407,49 @@ def test_observer_look_equals_east_north_up_geometry():
         daz = np.abs(az - az_ref)
         np.testing.assert_allclose(np.minimum(daz, 360.0 - daz), 0.0, atol=1e-7)
         np.testing.assert_allclose(el, el_ref, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------- ratio sharpening
+def _sharpen_fixture(dtype):
+    """satpy/tests/compositor_tests/test_resolution.py:33-70."""
+    low = (np.ones((2, 2)) + 4).astype(dtype)
+    low[1, 1] = 0.0
+    ds2 = (np.ones((2, 2)) + 2).astype(dtype)
+    ds3 = (np.ones((2, 2)) + 3).astype(dtype)
+    high = np.ones((2, 2), dtype)
+    high[1, 0] = np.nan
+    return low, ds2, ds3, high
+
+
+SHARPEN_CASES = [   # test_resolution.py:143-172
+    ("red", None, [[1.0, 1.0], [np.nan, 1.0]], [[0.6, 0.6], [np.nan, 3.0]], [[0.8, 0.8], [np.nan, 4.0]]),
+    ("red", "green", [[1.0, 1.0], [np.nan, 1.0]], [[3.0, 3.0], [np.nan, 3.0]], [[0.8, 0.8], [np.nan, 4.0]]),
+    ("green", None, [[5 / 3, 5 / 3], [np.nan, 0.0]], [[1.0, 1.0], [np.nan, 1.0]], [[4 / 3, 4 / 3], [np.nan, 4 / 3]]),
+    ("green", "blue", [[5 / 3, 5 / 3], [np.nan, 0.0]], [[1.0, 1.0], [np.nan, 1.0]], [[4.0, 4.0], [np.nan, 4.0]]),
+    ("blue", None, [[1.25, 1.25], [np.nan, 0.0]], [[0.75, 0.75], [np.nan, 0.75]], [[1.0, 1.0], [np.nan, 1.0]]),
+    ("blue", "red", [[5.0, 5.0], [np.nan, 0.0]], [[0.75, 0.75], [np.nan, 0.75]], [[1.0, 1.0], [np.nan, 1.0]]),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("hi,neutral,exp_r,exp_g,exp_b", SHARPEN_CASES)
+def test_ratio_sharpening_golden(hi, neutral, exp_r, exp_g, exp_b, dtype):
+    """satpy/tests/compositor_tests/test_resolution.py:173-191."""
+    from oracle import composites as oc
+    low, ds2, ds3, high = _sharpen_fixture(dtype)
+    data = oc.ratio_sharpened_rgb(low, ds2, ds3, high, hi, neutral)
+    assert data.dtype == dtype
+    for got, exp in zip(data, (exp_r, exp_g, exp_b)):
+        np.testing.assert_allclose(got, np.array(exp), rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_self_sharpened_golden(dtype):
+    """satpy/tests/compositor_tests/test_resolution.py:193-215."""
+    from oracle import composites as oc
+    low, ds2, ds3, _ = _sharpen_fixture(dtype)
+    data = oc.ratio_sharpened_rgb(low, ds2, ds3, None, "red", None, self_sharpen=True)
+    assert data.shape == (3, 2, 2) and data.dtype == dtype
+    np.testing.assert_allclose(data[0], [[5.0, 5.0], [5.0, 0]], rtol=1e-5)
+    np.testing.assert_allclose(data[1], [[4.0, 4.0], [4.0, 0]], rtol=1e-5)
+    np.testing.assert_allclose(data[2], [[16 / 3, 16 / 3], [16 / 3, 0]], rtol=1e-5)
