@@ -382,7 +382,11 @@ int b200_ll2cr(const b200_geo_t *swath, const b200_geo_t *dst, void *cols, void 
  * accumulation grids grid_weights / grid_accums ([nbands][grid_rows * grid_cols] float32, zeroed by the
  * caller before the first call; several calls -- e.g. one per scan chunk or per GPU -- accumulate).
  * rows_per_scan <= 0 means the whole swath is one scan.  img_fill: input value to skip (NaN always is).
- * In maximum_weight_mode all samples must come through ONE call. */
+ * maximum_weight_mode 1 keeps, per cell, the sample with the largest weight: all samples must come through ONE
+ * call.  To split the samples over several calls / ranks: mode 2 (only the maximum of the weights, into
+ * grid_weights), take the element-wise maximum of the weight grids, then mode 3 with that grid (writes the samples
+ * whose weight equals the maximum into grid_accums, NaN for an invalid sample) and combine the value grids -- see
+ * satpy_b200/resample/ewa.py::B200EWAResampler.compute(group=...). */
 int b200_fornav_accum(const void *cols, const void *rows, int32_t cr_is_f32, int64_t swath_rows,
                       int64_t swath_cols, int32_t rows_per_scan, const float *data, int32_t nbands,
                       int64_t band_stride, float img_fill, int64_t grid_rows, int64_t grid_cols,

@@ -65,6 +65,31 @@ def write_store(path, arrays, attrs=None):
         json.dump({"metadata": consolidated, "zarr_consolidated_format": 1}, fh)
 
 
+def write_root_array(path, arr):
+    """A store whose root IS the array (what ``dask.array.to_zarr(path)`` writes: satpy/modifiers/angles.py:207-213)."""
+    arr = np.ascontiguousarray(arr)
+    os.makedirs(path, exist_ok=True)
+    chunks = _chunk_shape(arr.shape, arr.dtype.itemsize)
+    fill = False if arr.dtype == np.bool_ else (0 if arr.dtype.kind in "iu" else "NaN")
+    with open(os.path.join(path, ".zarray"), "w") as fh:
+        json.dump({"chunks": list(chunks), "compressor": None, "dtype": arr.dtype.str, "fill_value": fill,
+                   "filters": None, "order": "C", "shape": list(arr.shape), "zarr_format": 2}, fh)
+    rows = chunks[0] if chunks else 1
+    tail = ".".join("0" for _ in arr.shape[1:])
+    for k, r0 in enumerate(range(0, arr.shape[0] if arr.shape else 1, rows)):
+        block = arr[r0:r0 + rows] if arr.shape else arr
+        if block.shape[0] < rows:
+            block = np.concatenate([block, np.zeros((rows - block.shape[0],) + block.shape[1:], dtype=arr.dtype)], axis=0)
+        with open(os.path.join(path, str(k) if not tail else f"{k}.{tail}"), "wb") as fh:
+            fh.write(np.ascontiguousarray(block).tobytes())
+
+
+def read_root_array(path):
+    """The array at the root of a store (see ``write_root_array``)."""
+    head, name = os.path.split(os.path.normpath(path))
+    return read_array(head, name)
+
+
 def _decode(raw, compressor):
     if compressor is None:
         return raw
@@ -80,7 +105,8 @@ def read_array(path, name):
     """One array of a zarr-v2 store as numpy (``IOError`` when the store or the array is missing / unreadable)."""
     try:
         import zarr
-        return np.array(zarr.open(path, mode="r")[name])
+        root = zarr.open(path, mode="r")
+        return np.array(root[name] if name else root)
     except ImportError:
         pass
     except (ValueError, KeyError) as err:  # the reference maps these to IOError too (kdtree.py:154-155)

@@ -242,6 +242,7 @@ extern "C" int b200_fornav_accum(const void *cols, const void *rows, int32_t cr_
     B200_CHECK_ARG(params->weight_count >= 2, "weight_count must be at least 2");
     B200_CHECK_ARG(params->weight_min > 0.0f, "weight_min must be greater than 0");
     B200_CHECK_ARG(params->weight_distance_max > 0.0f, "weight_distance_max must be greater than 0");
+    B200_CHECK_ARG(params->maximum_weight_mode >= 0 && params->maximum_weight_mode <= 3, "maximum_weight_mode must be 0..3");
     if (swath_rows * swath_cols == 0) return B200_OK;
     B200_CHECK_ARG(swath_cols >= 3, "fornav needs at least 3 swath columns");
     if (rows_per_scan <= 0) rows_per_scan = (int32_t)swath_rows;
@@ -284,12 +285,16 @@ extern "C" int b200_fornav_accum(const void *cols, const void *rows, int32_t cr_
         const int64_t n = swath_rows * swath_cols;
         ewa_params_kernel<<<b200_grid_for(nscans * swath_cols, 256, 8), 256, 0, s>>>(A, ewap);
         const int grid = b200_grid_for(n, 256, 8);
-        if (!params->maximum_weight_mode) {
+        // maximum_weight_mode: 1 = both passes; 2 = only the maxima of the weights, 3 = only the samples whose weight
+        // equals the maximum already in grid_weights -- so that several ranks can take the maximum of their weight
+        // grids in between (max-by-weight reduction)
+        const int mwm = params->maximum_weight_mode;
+        if (mwm == 0)
             fornav_kernel<0><<<grid, 256, 0, s>>>(A, ewap, data, nbands, band_stride, img_fill, grid_weights, grid_accums);
-        } else {
+        if (mwm == 1 || mwm == 2)
             fornav_kernel<1><<<grid, 256, 0, s>>>(A, ewap, data, nbands, band_stride, img_fill, grid_weights, grid_accums);
+        if (mwm == 1 || mwm == 3)
             fornav_kernel<2><<<grid, 256, 0, s>>>(A, ewap, data, nbands, band_stride, img_fill, grid_weights, grid_accums);
-        }
         e = cudaGetLastError();
     }
     if (wtab) cudaFreeAsync(wtab, s);

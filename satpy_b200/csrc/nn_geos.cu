@@ -96,6 +96,15 @@ __device__ __forceinline__ float nn_d2f(const float4 &p, float tx, float ty, flo
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
+// Euclidean grid distance from the fractional position (fc, fr) to the nearest lattice point OUTSIDE its 2 x 2 enclosing
+// block: 1 + the distance to the nearest edge of the block -- 1 for a target on an edge, 1.5 at the centre, which is
+// where the nearest pixel is farthest away.  (The first release compared against the worst case 1: every target whose
+// nearest pixel was more than 0.98 x 975 m away -- a third of config 5 -- took the disc search.)
+__device__ __forceinline__ float nn_block_clearance(float fc, float fr, int c0, int r0) {
+    const float fx = fc - (float)c0, fy = fr - (float)r0;
+    return 1.0f + fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy));
+}
+
 // EXACT search (float64 distances, float32 pre-filter).  Out of line: it only runs for the rare targets whose
 // float32 ranking below is ambiguous (equidistant pixels, neighbour at the radius).
 __device__ __noinline__ long long nn_fixed_search_exact(const GeosDev &G, float fc, float fr, double tx, double ty,
@@ -136,7 +145,7 @@ __device__ __noinline__ long long nn_fixed_search_exact(const GeosDev &G, float 
     // Any closer pixel lies inside the disc of radius w pixels around (fc, fr) (Euclidean bound above).
     const float bd = sqrtf((float)best.d2);
     const float w = bd * G.inv_step * 1.0001f + GEOS_POS_ERR;
-    if (w < 1.0f) return best.idx;  // every pixel outside the 2x2 block is at least one pixel away
+    if (w < nn_block_clearance(fc, fr, c0, r0)) return best.idx;  // no pixel outside the 2x2 block is that close
     {
         const float t = bd * 1.000001f + GEOS_F32_SLACK;
         thr2 = fminf(G.r2_slack, t * t * 1.000001f);
@@ -212,7 +221,7 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
     // best distance so far is at most sqrt(m1) + 1 m, and never needs to exceed the radius.
     const float bd = fminf(G.radius_f, sqrtf(m1) + GEOS_F32_ERR);
     const float w = bd * G.inv_step * 1.0001f + GEOS_POS_ERR;
-    if (w >= 1.0f) {  // else every pixel outside the 2x2 block is at least one pixel away
+    if (w >= nn_block_clearance(fc, fr, c0, r0)) {  // else no pixel outside the 2x2 block can be closer
         GEOS_CNT(1);
         if (!(m1 < inf)) GEOS_CNT(8);
         const float w2 = w * w;

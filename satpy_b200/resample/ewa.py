@@ -34,6 +34,20 @@ def ewa_params(weight_count=10000, weight_min=0.01, weight_distance_max=1.0, wei
     return p
 
 
+def max_weight_encode(accums):
+    """Value grid of ``maximum_weight_mode`` pass 2 on one rank -> what the ranks MAX-reduce: cells nobody on this rank
+    wrote hold -inf (the grid's initial value), a kept sample that is invalid (NaN) becomes +inf so that it survives
+    the reduction -- the sample with the largest weight decides, valid or not, as in the sequential loop."""
+    import torch
+    return torch.where(torch.isnan(accums), torch.full_like(accums, float("inf")), accums)
+
+
+def max_weight_decode(enc):
+    """After the MAX reduction: +-inf -> NaN (an invalid sample won / no sample reached the cell)."""
+    import torch
+    return torch.where(torch.isinf(enc), torch.full_like(enc, float("nan")), enc)
+
+
 def scan_band(height: int, rows_per_scan: int, scan_rows=None):
     """Validate a band of swath rows ``(row0, nrows)`` for fornav: it has to start on a scan boundary and hold whole
     scans (ellipse parameters are computed per scan).  ``None``: the whole swath."""
@@ -118,8 +132,6 @@ class B200EWAResampler(_compat.resampler_base()):
         if tuple(t.shape[-2:]) != src.shape:
             raise ValueError(f"data shape {tuple(t.shape)} does not end with the source shape {src.shape}")
         row0, nrows = scan_band(src.height, int(rows_per_scan), scan_rows)
-        if group is not None and maximum_weight_mode:
-            raise NotImplementedError("maximum_weight_mode over several ranks needs a max-by-weight reduction")
         lead = tuple(t.shape[:-2])
         nbands = int(np.prod(lead)) if lead else 1
         out = torch.empty(lead + dst.shape, dtype=torch.float32, device="cuda")
@@ -131,18 +143,37 @@ class B200EWAResampler(_compat.resampler_base()):
             p = ewa_params(weight_count, weight_min, weight_distance_max, weight_delta_max, weight_sum_min,
                            maximum_weight_mode)
             stream = _lib.stream_ptr(torch)
-            if nrows > 0:
-                cr_item = 4 if self._cr["f32"] else 8
-                first = row0 * src.width
+            cr_item = 4 if self._cr["f32"] else 8
+            first = row0 * src.width
+
+            def accumulate(mode):
+                if nrows <= 0:
+                    return
+                p.maximum_weight_mode = mode
                 _lib.check(lib.b200_fornav_accum(self._cr["cols"].data_ptr() + first * cr_item,
                                                  self._cr["rows"].data_ptr() + first * cr_item,
                                                  1 if self._cr["f32"] else 0, nrows, src.width, int(rows_per_scan),
                                                  t.data_ptr() + first * 4, nbands, src.size, float("nan"), dst.height,
                                                  dst.width, weights.data_ptr(), accums.data_ptr(), C.byref(p), stream))
-            if group is not None:
+            if group is None:
+                accumulate(1 if maximum_weight_mode else 0)
+            elif not maximum_weight_mode:
                 import torch.distributed as dist
+                accumulate(0)
                 dist.all_reduce(weights, op=dist.ReduceOp.SUM, group=group)
                 dist.all_reduce(accums, op=dist.ReduceOp.SUM, group=group)
+            else:
+                # max-by-weight reduction: the maxima of the weights over all ranks first, then every rank writes the
+                # samples that reach them, and the value grids are merged (see max_weight_encode)
+                import torch.distributed as dist
+                accumulate(2)
+                dist.all_reduce(weights, op=dist.ReduceOp.MAX, group=group)
+                accums.fill_(float("-inf"))
+                accumulate(3)
+                enc = max_weight_encode(accums)
+                dist.all_reduce(enc, op=dist.ReduceOp.MAX, group=group)
+                accums = max_weight_decode(enc)
+            p.maximum_weight_mode = 1 if maximum_weight_mode else 0
             counts = (C.c_int64 * nbands)()
             _lib.check(lib.b200_fornav_finalize(weights.data_ptr(), accums.data_ptr(), out.data_ptr(), nbands, dst.size,
                                                 C.byref(p), float(fill_value), counts, stream))

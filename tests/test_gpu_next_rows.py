@@ -311,3 +311,93 @@ def test_ratio_and_self_sharpened_rgb_golden_and_oracle(dtype):
     unmasked = SelfSharpenedRGB(name="t", common_channel_mask=False)(bands)
     exp = oc.ratio_sharpened_rgb(*bands, None, "red", None, self_sharpen=True, common_channel_mask=False)
     np.testing.assert_allclose(unmasked, exp, rtol=tol, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------- EWA maximum_weight_mode over ranks
+def test_fornav_maximum_weight_mode_split_over_two_emulated_ranks():
+    """The max-by-weight reduction of ``B200EWAResampler.compute(group=...)`` with the two ranks emulated on one GPU:
+    pass 1 per band (mode 2), element-wise maximum of the weight grids, pass 2 per band (mode 3), MAX of the encoded
+    value grids -- equals the single-call ``maximum_weight_mode`` result up to equal-weight ties."""
+    import ctypes as C
+    import torch
+    from satpy_b200 import AreaDefinition, SwathDefinition, _lib
+    from satpy_b200.resample import B200EWAResampler
+    from satpy_b200.resample.ewa import ewa_params, max_weight_decode, max_weight_encode, scan_bands
+    lon, lat, rps = demo.viirs_like_swath(bowtie=0.3)
+    proj = {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 0.0, "ellps": "WGS84"}
+    dst = AreaDefinition("ps", "ps", "ps", proj, 300, 300, (-1.2e6, -2.4e6, 0.3e6, -0.9e6))
+    rng = np.random.default_rng(4)
+    data = rng.uniform(0, 120, size=lon.shape).astype(np.float32)
+    data[rng.random(lon.shape) < 0.02] = np.nan
+    r = B200EWAResampler(SwathDefinition(lon, lat), dst)
+    whole = r.compute(data, rows_per_scan=rps, maximum_weight_mode=True)
+    lib = _lib.load()
+    stream = _lib.stream_ptr(torch)
+    t = torch.from_numpy(data).cuda()
+    src = r.source_geo_def
+    bands = scan_bands(lon.shape[0], rps, 2)
+    item = 4 if r._cr["f32"] else 8
+
+    def accum(row0, nrows, mode, weights, accums):
+        p = ewa_params(maximum_weight_mode=True)
+        p.maximum_weight_mode = mode
+        first = row0 * src.width
+        _lib.check(lib.b200_fornav_accum(r._cr["cols"].data_ptr() + first * item, r._cr["rows"].data_ptr() + first * item,
+                                         1 if r._cr["f32"] else 0, nrows, src.width, rps, t.data_ptr() + first * 4, 1,
+                                         src.size, float("nan"), dst.height, dst.width, weights.data_ptr(),
+                                         accums.data_ptr(), C.byref(p), stream))
+    ws = [torch.zeros(dst.shape, dtype=torch.float32, device="cuda") for _ in bands]
+    dummy = torch.zeros(dst.shape, dtype=torch.float32, device="cuda")
+    for (row0, nrows), w in zip(bands, ws):
+        accum(row0, nrows, 2, w, dummy)
+    wmax = torch.maximum(ws[0], ws[1])
+    encs = []
+    for row0, nrows in bands:
+        a = torch.full(dst.shape, float("-inf"), dtype=torch.float32, device="cuda")
+        accum(row0, nrows, 3, wmax.clone(), a)
+        encs.append(max_weight_encode(a))
+    merged = max_weight_decode(torch.maximum(encs[0], encs[1]))
+    out = torch.empty(dst.shape, dtype=torch.float32, device="cuda")
+    p = ewa_params(maximum_weight_mode=True)
+    _lib.check(lib.b200_fornav_finalize(wmax.data_ptr(), merged.data_ptr(), out.data_ptr(), 1, dst.size, C.byref(p),
+                                        float("nan"), None, stream))
+    got = out.cpu().numpy()
+    assert (np.isnan(got) != np.isnan(whole)).mean() < 1e-3
+    ok = ~np.isnan(got) & ~np.isnan(whole)
+    assert ok.mean() > 0.3 and (got[ok] != whole[ok]).mean() < 2e-3
+
+
+# ------------------------------------------------------------------------------- sensor-angle caching
+def test_sensor_angles_are_cached_on_the_device_and_as_zarr(tmp_path):
+    """``cache_sensor_angles`` (satpy/modifiers/angles.py:53-213,321-333): sensor angles computed once per (area,
+    rounded satellite position), kept on the device and persisted as zarr stores with the reference's file-name
+    pattern; the sun angles are evaluated per scene."""
+    import datetime as dt
+    import torch
+    from satpy_b200.modifiers import angles
+    area = demo.make_area("goes_east_abi_f_2km", 400 / 5424)
+    t1, t2 = dt.datetime(2019, 3, 14, 18, 0), dt.datetime(2019, 3, 14, 21, 0)
+    pos = dict(sat_lon=-75.23, sat_lat=0.04, sat_alt=35786023.7)
+    angles.sensor_angle_cache_clear(str(tmp_path))
+    plain = angles.get_angles(area=area, start_time=t1, sat_lon=-75.2, sat_lat=0.0, sat_alt=35786023.7, device=True)
+    a1 = angles.get_angles(area=area, start_time=t1, device=True, cache_sensor_angles=True, cache_dir=str(tmp_path), **pos)
+    for got, exp in zip(a1, plain):       # cached = computed with the position rounded to one decimal
+        np.testing.assert_allclose(got.cpu().numpy(), exp.cpu().numpy(), rtol=0, atol=1e-9, equal_nan=True)
+    stores = sorted(p.name for p in tmp_path.glob("_get_sensor_angles_from_sat_pos_v1_*_*.zarr"))
+    assert len(stores) == 2 and "_v1_0_" in stores[0] and "_v1_1_" in stores[1]
+    a2 = angles.get_angles(area=area, start_time=t2, device=True, cache_sensor_angles=True, cache_dir=str(tmp_path), **pos)
+    assert a2[0] is a1[0] and a2[1] is a1[1]                       # device-resident
+    assert not torch.equal(torch.nan_to_num(a2[3]), torch.nan_to_num(a1[3]))   # the sun moved
+    angles._SENSOR_ANGLE_CACHE.clear()                              # a new process: read the stores back
+    a3 = angles.get_angles(area=area, start_time=t2, device=True, cache_sensor_angles=True, cache_dir=str(tmp_path), **pos)
+    assert a3[0] is not a1[0]
+    np.testing.assert_array_equal(a3[0].cpu().numpy(), a1[0].cpu().numpy())
+    np.testing.assert_array_equal(a3[1].cpu().numpy(), a1[1].cpu().numpy())
+    angles.config["cache_sensor_angles"], angles.config["cache_dir"] = True, str(tmp_path)
+    try:
+        satz = angles.get_satellite_zenith_angle(area=area, start_time=t1, device=True, **pos)
+        assert satz is a3[1]
+    finally:
+        angles.config["cache_sensor_angles"], angles.config["cache_dir"] = False, None
+    angles.sensor_angle_cache_clear(str(tmp_path))
+    assert not list(tmp_path.glob("*.zarr")) and not angles._SENSOR_ANGLE_CACHE

@@ -265,6 +265,65 @@ def test_ewa_scan_bands_sum_to_the_whole_world_size_2_gloo(tmp_path):
     assert "EWA_GLOO_OK" in out.stdout
 
 
+_EWA_MAX_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from oracle import ewa as oewa
+from oracle.projections import Area
+from satpy_b200 import demo
+from satpy_b200.resample.ewa import scan_bands, max_weight_encode, max_weight_decode
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lon, lat, rps = demo.viirs_like_swath(nscans=6, ncols=120, bowtie=0.3)
+proj = {"proj": "stere", "lat_0": 90.0, "lat_ts": 60.0, "lon_0": 0.0, "ellps": "WGS84"}
+dst = Area(proj, 60, 60, (-1.2e6, -2.4e6, 0.3e6, -0.9e6))
+_, cols, rows = oewa.ll2cr(lon, lat, dst)
+rng = np.random.default_rng(2)
+data = rng.uniform(0, 100, lon.shape).astype(np.float32)
+data[rng.random(lon.shape) < 0.05] = np.nan
+row0, nrows = scan_bands(lon.shape[0], rps, world)[rank]
+sl = slice(row0, row0 + nrows)
+# what one rank holds after its two passes: the maxima of ITS weights, then -- given the maxima over all ranks -- the
+# samples that reach them (-inf where none of its samples does, NaN for an invalid sample)
+_, _, w, a = oewa.fornav(cols[sl], rows[sl], (60, 60), data[sl], rows_per_scan=rps, maximum_weight_mode=True,
+                         return_grids=True)
+tw = torch.from_numpy(w[0].copy())
+dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+mine = torch.from_numpy(a[0].copy())
+mine = torch.where(torch.from_numpy(w[0]) == tw, mine, torch.full_like(mine, float("-inf")))
+mine = torch.where(tw > 0, mine, torch.full_like(mine, float("-inf")))
+enc = max_weight_encode(mine)
+dist.all_reduce(enc, op=dist.ReduceOp.MAX)
+merged = max_weight_decode(enc).numpy()
+_, _, w_all, a_all = oewa.fornav(cols, rows, (60, 60), data, rows_per_scan=rps, maximum_weight_mode=True,
+                                 return_grids=True)
+np.testing.assert_array_equal(tw.numpy(), w_all[0])
+hit = w_all[0] > 0
+same = (merged[hit] == a_all[0][hit]) | (np.isnan(merged[hit]) & np.isnan(a_all[0][hit]))
+assert same.mean() > 0.995, same.mean()          # equal maximum weights in two bands: either sample is "the" maximum
+assert np.isnan(merged[~hit]).all()
+dist.barrier()
+if rank == 0:
+    print("EWA_MAX_GLOO_OK", int(hit.sum()), float(same.mean()))
+dist.destroy_process_group()
+'''
+
+
+def test_ewa_maximum_weight_mode_reduces_by_weight_world_size_2_gloo(tmp_path):
+    """Multi-GPU EWA in ``maximum_weight_mode`` (SURVEY.md 8e): MAX-reduce the weight grids, keep the samples that reach
+    the global maxima, MAX-reduce the encoded value grids (``max_weight_encode`` / ``_decode``); checked with the
+    oracle's grids on two gloo ranks against the whole-swath result."""
+    script = tmp_path / "worker.py"
+    script.write_text(_EWA_MAX_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29635", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "EWA_MAX_GLOO_OK" in out.stdout
+
+
 def test_peer_exchange_rounds_are_collision_free():
     """PeerImage's schedule: in every round the destinations form a permutation without fixed points, and over the
     world_size - 1 rounds every rank reaches every peer exactly once."""
