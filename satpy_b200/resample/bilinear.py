@@ -13,11 +13,14 @@ Parity is UNPINNED in the reference (its tests mock the library); see oracle/bil
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
+import json
 import logging
+import os
 
 import numpy as np
 
-from .. import _compat, _lib, _xfer
+from .. import _compat, _lib, _xfer, _zarr2
 from ..dataset import is_dataarray, payload, rewrap
 from ..geometry import AreaDefinition, as_geometry
 from .nearest import SEARCH_METHODS, _Grid
@@ -38,10 +41,12 @@ class B200BilinearResampler(_compat.resampler_base()):
 
     def precompute(self, mask=None, radius_of_influence=50000, epsilon=0, reduce_data=True, cache_dir=False,
                    neighbours=32, row_window=None, **kwargs):
-        """``get_bil_info``.  ``mask``, ``epsilon``, ``reduce_data`` and ``cache_dir`` are accepted for signature
-        compatibility (the reference deletes ``mask`` too, kdtree.py:224); the search is exact and the coefficients
-        are cached on this instance."""
-        del kwargs, mask, epsilon, reduce_data, cache_dir
+        """``get_bil_info``.  ``mask`` is deleted exactly as the reference does (``del mask``, kdtree.py:224);
+        ``epsilon`` and ``reduce_data`` are accepted for signature compatibility (the search is exact and always reads
+        only the source pixels around each target).  The coefficients are cached on this instance and, with
+        ``cache_dir``, loaded from / saved to ``bil_lut-<hash>.zarr`` (``load_bil_info`` / ``save_bil_info``,
+        kdtree.py:244-279)."""
+        del kwargs, mask, epsilon, reduce_data
         torch = _lib.require_cuda()
         lib = _lib.load()
         src, dst = self.source_geo_def, self.target_geo_def
@@ -53,6 +58,13 @@ class B200BilinearResampler(_compat.resampler_base()):
         if self._info is not None and self._info["key"] == key:
             LOG.debug("Reusing device-resident bilinear parameters")
             return key
+        if cache_dir and row_window is None:
+            try:
+                self.load_bil_info(cache_dir, radius_of_influence=radius, neighbours=int(neighbours))
+                LOG.debug("Loaded bilinear parameters")
+                return key
+            except IOError:
+                pass
         LOG.debug("Computing bilinear parameters")
         stream = _lib.stream_ptr(torch)
         valid_input = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
@@ -76,7 +88,67 @@ class B200BilinearResampler(_compat.resampler_base()):
         self._info = {"key": key, "bilinear_t": t, "bilinear_s": s, "index_array": index_array,
                       "gather_index": gather_index, "valid_input_index": valid_input, "n_valid": int(n_valid.value),
                       "out_shape": (nrows, dst.width)}
+        if cache_dir and row_window is None:
+            LOG.debug("Saving bilinear parameters.")
+            self.save_bil_info(cache_dir, radius_of_influence=radius, neighbours=int(neighbours))
         return key
+
+    # --------------------------------------------------------------- cache on disk
+    def _cache_filename(self, cache_dir, radius_of_influence, neighbours):
+        """``bil_lut-<hash>.zarr`` (kdtree.py:244-279): pyresample's own naming inside satpy, a sha1 over the two
+        geometries and the keywords stand-alone."""
+        create = getattr(super(), "_create_cache_filename", None)
+        if create is not None:
+            try:
+                return create(cache_dir, prefix="bil_lut-", radius_of_influence=radius_of_influence,
+                              neighbours=neighbours, epsilon=0)
+            except Exception:  # noqa: BLE001
+                pass
+        src, dst = self.source_geo_def, self.target_geo_def
+        key = json.dumps({"src": [sorted((k, str(v)) for k, v in src.proj_dict.items()), src.shape, src.area_extent],
+                          "dst": [sorted((k, str(v)) for k, v in dst.proj_dict.items()), dst.shape, dst.area_extent],
+                          "radius_of_influence": radius_of_influence, "neighbours": neighbours}, sort_keys=True)
+        return os.path.join(cache_dir, "bil_lut-" + hashlib.sha1(key.encode()).hexdigest() + ".zarr")
+
+    def save_bil_info(self, cache_dir, radius_of_influence=50000.0, neighbours=32):
+        """Persist the coefficients as a zarr-v2 store: ``bilinear_t`` / ``bilinear_s`` (float64, N), ``index_array``
+        (int64, N x 4: the four corners, compressed valid-input indices) and ``valid_input_index`` (bool, source
+        shape) -- the quantities pyresample's ``save_resampling_info`` stores (its own array names for the corner
+        indices could not be checked: pyresample is not installable here)."""
+        if not cache_dir or self._info is None:
+            return None
+        os.makedirs(cache_dir, exist_ok=True)
+        filename = self._cache_filename(cache_dir, float(radius_of_influence), int(neighbours))
+        info = self.bil_info()
+        _zarr2.write_store(filename, {"bilinear_t": (("x1",), info["bilinear_t"]), "bilinear_s": (("x1",), info["bilinear_s"]),
+                                      "index_array": (("x1", "n"), info["index_array"].astype(np.int64)),
+                                      "valid_input_index": (("y2", "x2"), info["valid_input_index"])})
+        LOG.info("Saving BIL neighbour info to %s", filename)
+        return filename
+
+    def load_bil_info(self, cache_dir, radius_of_influence=50000.0, neighbours=32):
+        """Re-install coefficients saved earlier; ``IOError`` when the cache has no entry (kdtree.py:244-258)."""
+        if not cache_dir:
+            raise IOError
+        torch = _lib.require_cuda()
+        filename = self._cache_filename(cache_dir, float(radius_of_influence), int(neighbours))
+        if not os.path.isdir(filename):
+            raise IOError(f"no cached bilinear info {filename}")
+        src, dst = self.source_geo_def, self.target_geo_def
+        t = torch.from_numpy(_zarr2.read_array(filename, "bilinear_t")).to("cuda")
+        s_ = torch.from_numpy(_zarr2.read_array(filename, "bilinear_s")).to("cuda")
+        idx = torch.from_numpy(_zarr2.read_array(filename, "index_array")).to("cuda").to(torch.int32).contiguous()
+        vin = torch.from_numpy(_zarr2.read_array(filename, "valid_input_index").astype(np.uint8)).to("cuda")
+        if tuple(vin.shape) != src.shape or t.numel() != dst.size or tuple(idx.shape) != (dst.size, 4):
+            raise IOError("cached bilinear info does not match the geometries")
+        # compressed -> raw source indices for the gather (the kernel works on raw pixel numbers)
+        gi = torch.empty_like(idx)
+        _lib.check(_lib.load().b200_nn_compressed_to_raw(vin.data_ptr(), vin.numel(), idx.data_ptr(), gi.data_ptr(),
+                                                         idx.numel(), _lib.stream_ptr(torch)))
+        self._info = {"key": (float(radius_of_influence), int(neighbours), 0, dst.height), "bilinear_t": t,
+                      "bilinear_s": s_, "index_array": idx, "gather_index": gi, "valid_input_index": vin,
+                      "n_valid": int(vin.sum().item()), "out_shape": dst.shape}
+        return filename
 
     def bil_info(self, as_numpy=True):
         if self._info is None:

@@ -401,3 +401,29 @@ def test_sensor_angles_are_cached_on_the_device_and_as_zarr(tmp_path):
         angles.config["cache_sensor_angles"], angles.config["cache_dir"] = False, None
     angles.sensor_angle_cache_clear(str(tmp_path))
     assert not list(tmp_path.glob("*.zarr")) and not angles._SENSOR_ANGLE_CACHE
+
+
+def test_bilinear_cache_dir_round_trip(tmp_path):
+    """``cache_dir`` for the bilinear coefficients (satpy/resample/kdtree.py:216-279): a second resampler loads
+    ``bil_lut-<hash>.zarr`` instead of searching and gives the same image."""
+    import json
+    from satpy_b200 import AreaDefinition
+    from satpy_b200.resample import B200BilinearResampler
+    src = demo.make_area("goes_east_abi_f_2km", 300 / 5424)
+    proj = {"proj": "lcc", "lat_1": 25.0, "lat_2": 45.0, "lat_0": 35.0, "lon_0": -95.0, "ellps": "WGS84"}
+    dst = AreaDefinition("lcc", "lcc", "lcc", proj, 120, 100, (-2.6e6, -2.2e6, 2.6e6, 2.2e6))
+    data = np.random.default_rng(3).uniform(200, 320, size=src.shape).astype(np.float32)
+    r1 = B200BilinearResampler(src, dst)
+    out1 = r1.resample(data, radius_of_influence=100e3, cache_dir=str(tmp_path), fill_value=np.nan)
+    stores = list(tmp_path.glob("bil_lut-*.zarr"))
+    assert len(stores) == 1
+    assert json.load(open(stores[0] / "bilinear_t" / ".zarray"))["dtype"] == "<f8"
+    assert json.load(open(stores[0] / "index_array" / ".zarray"))["shape"] == [dst.size, 4]
+    r2 = B200BilinearResampler(src, dst)
+    r2.load_bil_info(str(tmp_path), radius_of_influence=100e3)
+    np.testing.assert_array_equal(r2.compute(data, fill_value=np.nan), out1)
+    r3 = B200BilinearResampler(src, dst)
+    np.testing.assert_array_equal(r3.resample(data, radius_of_influence=100e3, cache_dir=str(tmp_path),
+                                              fill_value=np.nan), out1)
+    with pytest.raises(IOError):
+        B200BilinearResampler(src, dst).load_bil_info(str(tmp_path), radius_of_influence=101e3)
