@@ -7,7 +7,7 @@ import pytest
 
 from oracle import calibration as ocal
 from oracle import solar as osolar
-from satpy_b200 import AreaDefinition, DataArrayLite
+from satpy_b200 import AreaDefinition, DataArrayLite, demo
 from satpy_b200.modifiers import SunZenithReducer, sunz_reduce
 from satpy_b200.readers import AHICalibration, SEVIRICalibration, calibrate_ahi, calibrate_seviri, scale_viirs
 
@@ -256,7 +256,7 @@ def test_ratio_and_self_sharpened_rgb_golden_and_oracle(dtype):
     from satpy_b200 import DataArrayLite
     from satpy_b200.composites import RatioSharpenedRGB, SelfSharpenedRGB
     from satpy_b200.modifiers import IncompatibleAreas
-    from tests.test_oracle_golden import SHARPEN_CASES, _sharpen_fixture
+    from .test_oracle_golden import SHARPEN_CASES, _sharpen_fixture
     low, ds2, ds3, high = _sharpen_fixture(dtype)
     attrs = {"resolution": 1000, "calibration": "reflectance", "units": "%", "name": "test_vis"}
     mk = lambda a, **kw: DataArrayLite(a, ("y", "x"), dict(attrs, **kw))   # noqa: E731
