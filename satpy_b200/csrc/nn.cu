@@ -626,6 +626,12 @@ nn_target_tables_kernel(const __grid_constant__ TableArg A, TgtCol *__restrict__
                     double rr = A.rp / hypot(A.rp * cos(pg), sin(pg));
                     t.rc = (float)(rr * cos(pg));
                     t.rs = (float)(rr * sin(pg));
+                    // fixed-grid mode has no use for the search-cap fields: they carry the row's part of the target's
+                    // spherical point instead (R cos(phi), R sin(phi) in float64, the latter also rounded to float32),
+                    // so that the query kernel does one float64 multiplication per coordinate, not two
+                    t.dlam = B200_R_EARTH * t.cos_phi;
+                    t.dlam1 = B200_R_EARTH * t.sin_phi;
+                    t.b_lo = __float_as_int((float)t.dlam1);
                 } else {
                     t.dlam = nn_cap_dlam(t.phi, A.theta, A.sin_theta);
                     t.b_lo = b200_band_of(t.phi - A.theta, A.phi0, A.inv_dphi, A.nbands);

@@ -53,9 +53,13 @@ int b200_nn_fixed_grid_supported(const b200_geo_t *src) {
     if (src->is_swath || src->area.proj.kind != B200_PROJ_GEOS) return 0;
     const b200_proj_t &P = src->area.proj;
     // full-disk scan angles stay below ~0.152 rad; keep well inside the regime the bound was derived for
-    double ang_x = fabs(src->area.x_ul) / (P.p[0] * P.a) + src->area.pixel_size_x * src->area.width / (P.p[0] * P.a);
-    double ang_y = fabs(src->area.y_ul) / (P.p[0] * P.a) + src->area.pixel_size_y * src->area.height / (P.p[0] * P.a);
-    if (!(ang_x < 0.5) || !(ang_y < 0.5)) return 0;
+    // largest scan angle of the grid (pixel centres, relative to the sub-satellite point): full disks stay below
+    // 0.152 rad; nn_atan_scan's series and the 0.975 distance bound are good up to tan = 0.25
+    const double hm = P.p[0] * P.a;
+    const double x0 = src->area.x_ul - P.x0, x1 = x0 + src->area.pixel_size_x * (double)(src->area.width - 1);
+    const double y0 = src->area.y_ul - P.y0, y1 = y0 - src->area.pixel_size_y * (double)(src->area.height - 1);
+    const double ang_x = fmax(fabs(x0), fabs(x1)) / hm, ang_y = fmax(fabs(y0), fabs(y1)) / hm;
+    if (!(ang_x < 0.24) || !(ang_y < 0.24)) return 0;
     if (!(P.p[0] > 3.0)) return 0;  // satellite height > 3 earth radii (geostationary: 5.6)
     return 1;
 }
@@ -176,6 +180,13 @@ __device__ __noinline__ long long nn_fixed_search_exact(const GeosDev &G, float 
     return best.idx;
 }
 
+// MUFU.SQRT: 2^-22 relative (5e-4 m at 2 km), far inside the 0.01 m and 1e-4 relative slack of every test it feeds
+__device__ __forceinline__ float nn_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // two smallest float32 squared distances seen so far, branch-free.  Invalid pixels are stored as (+inf, 0, 0) in the
 // float32 copy, so their distance is +inf: it never becomes the minimum and leaves the runner-up at +inf.
 __device__ __forceinline__ void nn_track(float d, int idx, float &m1, int &i1, float &m2) {
@@ -207,7 +218,7 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
         const bool rk0 = (unsigned)r0 < (unsigned)G.H, rk1 = (unsigned)(r0 + 1) < (unsigned)G.H;
         const bool ck0 = (unsigned)c0 < (unsigned)G.W, ck1 = (unsigned)(c0 + 1) < (unsigned)G.W;
         const int i00 = r0 * G.W + c0;
-        const float4 *q00 = G.pts32 + (long long)r0 * G.W + c0, *q10 = q00 + G.W;
+        const float4 *q00 = G.pts32 + i00, *q10 = q00 + G.W;   // n_src < 2^31 (checked at build)
         if (rk0 && ck0) p00 = __ldg(q00);
         if (rk0 && ck1) p01 = __ldg(q00 + 1);
         if (rk1 && ck0) p10 = __ldg(q10);
@@ -219,7 +230,7 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
     }
     // Any closer pixel lies inside the disc of radius w pixels around (fc, fr) (Euclidean bound above); the exact
     // best distance so far is at most sqrt(m1) + 1 m, and never needs to exceed the radius.
-    const float bd = fminf(G.radius_f, sqrtf(m1) + GEOS_F32_ERR);
+    const float bd = fminf(G.radius_f, nn_sqrt_approx(m1) + GEOS_F32_ERR);
     const float w = bd * G.inv_step * 1.0001f + GEOS_POS_ERR;
     if (w >= nn_block_clearance(fc, fr, c0, r0)) {  // else no pixel outside the 2x2 block can be closer
         GEOS_CNT(1);
@@ -273,20 +284,20 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
             int jlo = 0, jhi = -1;
             if (!(lb >= B2 * 1.0001f)) {
                 GEOS_CNT(3);
-                const float hb = B * sqrtf(gcc * inv_det);
+                const float hb = B * nn_sqrt_approx(gcc * inv_det);
                 jlo = max(rlo, r0 + (int)ceilf(fy - hb)), jhi = min(rhi, r0 + (int)floorf(fy + hb));
             }
             for (int r = jlo; r <= jhi; ++r) {
                 const float b = (float)(r - r0) - fy;
                 const float disc = gcr * b * gcr * b - gcc * (grr * b * b - B2);
                 if (!(disc >= 0.0f)) continue;
-                const float sq = sqrtf(disc), mid = -gcr * b;
+                const float sq = nn_sqrt_approx(disc), mid = -gcr * b;
                 int clo = c0 + (int)ceilf(fx + (mid - sq) * inv_gcc), chi = c0 + (int)floorf(fx + (mid + sq) * inv_gcc);
                 // never outside the rigorous disc / the grid
                 const float dr = fr - (float)r;
                 const float wc2 = w2 - dr * dr;
                 if (!(wc2 >= 0.0f)) continue;
-                const float wc = sqrtf(wc2);
+                const float wc = nn_sqrt_approx(wc2);
                 clo = max(clo, max(0, (int)ceilf(fc - wc)));
                 chi = min(chi, min(G.W - 1, (int)floorf(fc + wc)));
                 const bool block_row = (r == r0) || (r == r0 + 1);
@@ -305,7 +316,7 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
                 const float dr = fr - (float)r;
                 const float wc2 = w2 - dr * dr;
                 if (!(wc2 >= 0.0f)) continue;
-                const float wc = sqrtf(wc2);
+                const float wc = nn_sqrt_approx(wc2);
                 const int clo = max(0, (int)ceilf(fc - wc)), chi = min(G.W - 1, (int)floorf(fc + wc));
                 const bool block_row = (r == r0) || (r == r0 + 1);
                 const int row_base = r * G.W;
@@ -322,7 +333,7 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
         GEOS_CNT(10);
         return -1;  // no valid pixel anywhere near
     }
-    const float s1 = sqrtf(m1);
+    const float s1 = nn_sqrt_approx(m1);
     const float t = s1 + 2.0f * GEOS_F32_ERR + 0.01f;
     const bool clear_winner = m2 > t * t * 1.000001f;
     const bool clear_radius = fabsf(s1 - G.radius_f) > GEOS_F32_ERR + 0.01f;
@@ -338,15 +349,14 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
 // atan for scan angles: a full disk stays below tan = 0.16, where the odd series to x^11 is exact to float32
 // (next term x^12 / 13 < 5e-9 relative at 0.25); anything larger takes the library routine.
 __device__ __forceinline__ float nn_atan_scan(float x) {
-    if (fabsf(x) < 0.25f) {
-        const float z = x * x;
-        float p = fmaf(z, -1.0f / 11.0f, 1.0f / 9.0f);
-        p = fmaf(z, p, -1.0f / 7.0f);
-        p = fmaf(z, p, 0.2f);
-        p = fmaf(z, p, -1.0f / 3.0f);
-        return fmaf(x * z, p, x);
-    }
-    return atanf(x);
+    // |x| < 0.25 always: b200_nn_fixed_grid_supported admits sources whose scan angles stay below 0.24 rad, and every
+    // point of the earth -- visible or just behind the limb -- is seen inside the disk's angular radius
+    const float z = x * x;
+    float p = fmaf(z, -1.0f / 11.0f, 1.0f / 9.0f);
+    p = fmaf(z, p, -1.0f / 7.0f);
+    p = fmaf(z, p, 0.2f);
+    p = fmaf(z, p, -1.0f / 3.0f);
+    return fmaf(x * z, p, x);
 }
 
 // target lon/lat -> fractional position in the source grid (PROJ geos forward, float32); false: far side.
@@ -515,12 +525,11 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
             long long raw = -1;
             float fc, fr;
             if (ok && nn_fixed_position(Q.G, R.rc, R.rs, Cc.s_rel, Cc.c_rel, fc, fr)) {
-                double tx = B200_R_EARTH * R.cos_phi * Cc.cos_lam;
-                double ty = B200_R_EARTH * R.cos_phi * Cc.sin_lam;
-                double tz = B200_R_EARTH * R.sin_phi;
+                // R.dlam = R_earth cos(phi), R.dlam1 = R_earth sin(phi), R.b_lo = float32 bits of the latter (nn.cu)
+                const double tx = R.dlam * Cc.cos_lam, ty = R.dlam * Cc.sin_lam;
                 bool need_exact;
-                raw = nn_fixed_search(Q.G, fc, fr, (float)tx, (float)ty, (float)tz, need_exact);
-                if (need_exact) raw = nn_fixed_search_exact(Q.G, fc, fr, tx, ty, tz);
+                raw = nn_fixed_search(Q.G, fc, fr, (float)tx, (float)ty, __int_as_float(R.b_lo), need_exact);
+                if (need_exact) raw = nn_fixed_search_exact(Q.G, fc, fr, tx, ty, R.dlam1);
             }
             if (FUSED1)
                 st_stream_f1(Q.O.out + i, raw < 0 ? Q.O.fill : __ldg(Q.O.data + raw));
