@@ -6,19 +6,28 @@
 Workload (BASELINE.json configs[4], the configuration the metric is quoted on; it fits one GPU):
 synthetic ABI C02 10848 x 10848 int16 counts on ``goes_east_abi_f_1km`` -> reflectance [%] ->
 SunZenithCorrector -> nearest-neighbour to the 0.5 km global equirectangular grid 80150 x 40075
-(3212 Mpix, 12.85 GB float32), radius_of_influence 2000 m.  One "step" is one full pass:
-fused calibrate+sunz kernel, search-structure build, fused query+gather, (N > 1) assembly of the image on
-every rank.  With N GPUs the target rows are cut into N x subtiles blocks handed out round-robin, each block
-fed only the source rows that can reach it; a finished block is pushed into every peer's copy of the image by
-the copy engines over NVLink (symmetric memory, ``--exchange p2p``) -- or every group of N blocks is
-all-gathered in place by NCCL (``--exchange nccl``) -- while the next block is searched (strong scaling: the
-total work is fixed).  The all-gather result is verified after the timed region (``exchange.verified``).
+(3212 Mpix, 12.85 GB float32), radius_of_influence 2000 m.
 
-One JSON line is printed by rank 0 (see the keys in ``main``).  ``value`` is whole-job output Mpix/s
-with inputs resident in HBM; ``e2e`` is the same through the public host-buffer API with the
-host<->device copies inside the timed region.  ``--impl reference`` times the CPU oracle (numpy/scipy
-restatement of the satpy/pyresample path -- satpy itself cannot be installed in this image, see
-DESIGN.md) on a bounded sample of the same workload with all host threads.
+One "step" is one full pass through the PUBLIC plug-in classes, exactly what a satpy user reaches:
+``calibrate_abi(counts, ..., "reflectance")`` -> ``SunZenithCorrector(...)([dataset])`` ->
+``B200NearestResampler(src, dst).resample(dataset, radius_of_influence=2000, fill_value=nan)`` with a FRESH
+resampler every step (cold search every step, no cached neighbour info).  ``value`` runs that flow with the
+counts resident in HBM and the image left in HBM; ``e2e`` runs the same calls with numpy counts in and a numpy
+image out (host<->device copies inside the timed region).
+
+With N GPUs the target rows are cut into N x subtiles blocks handed out round-robin; each block is a smaller
+scene (the source AREA is cropped to the rows that can reach the block, like ``Scene._reduce_data``).  Only the
+column span of a block that the disk can reach at all is pushed into the peers' copies of the image by the copy
+engines over NVLink (symmetric memory, ``--exchange p2p``), every rank writes the fill value elsewhere itself --
+or every group of N blocks is all-gathered in place by NCCL (``--exchange nccl``) -- while the next block is
+searched (strong scaling: the total work is fixed).  The assembled image is verified on every rank after the
+timed region (``exchange.verified``).
+
+One JSON line is printed by rank 0 (keys in ``run_b200``): ``stages`` holds every target kernel with its
+algorithmic bytes (in situ on the plug-in path and stand-alone at its BASELINE size), ``parity`` the comparison
+of the device image's rows with what the CPU arm computed for its sample tiles.  ``--impl reference`` times the
+CPU oracle (numpy/scipy restatement of the satpy/pyresample path -- satpy itself cannot be installed in this
+image) on a bounded sample of the same workload with all host threads.
 """
 from __future__ import annotations
 
@@ -506,7 +515,7 @@ def run_b200(args):
                "pcie_gbs": (h2d + d2h) / ms_e2e / 1e6,
                "note": "per rank: calibrate_abi(numpy counts) -> SunZenithCorrector -> B200NearestResampler.resample("
                        "to_host=True) -> numpy image of this rank's rows in page-locked memory; the rows are produced in "
-                       "8 bands, each copied out while the next is searched; of every band only the column span the disk "
+                       "24 bands, each copied out while the next is searched; of every band only the column span the disk "
                        "can reach crosses PCIe (d2h_bytes_per_step), host threads write the fill value into the rest of "
                        "the image (host_image_bytes_per_step is the whole image); bytes are per rank"}
         if world == 1 and args.scale == 1.0:

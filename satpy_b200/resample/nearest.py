@@ -105,7 +105,7 @@ class _Grid:
 class B200NearestResampler(_compat.resampler_base()):
     """Nearest-neighbour resampling on one B200."""
 
-    ROW_CHUNKS = 8   # host results: rows are produced in this many bands, each copied out while the next is computed
+    ROW_CHUNKS = 24  # host results: rows are produced in this many bands, each copied out while the next is computed
     trace = None     # set to a list to collect (stage, start event, end event) of the fused path (bench.py)
 
     def __init__(self, source_geo_def, target_geo_def):

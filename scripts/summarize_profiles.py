@@ -20,8 +20,9 @@ import shutil
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STEP_KERNELS = ("geos_tables_kernel", "abi_vis_sunz_kernel", "nn_source_points_kernel", "DeviceScanInitKernel",
-                "DeviceScanKernel", "nn_target_tables_kernel", "nn_seg_cmax_kernel", "nn_fixed_query_rect_kernel<1>")
+STEP_KERNELS = ("geos_tables_kernel", "abi_calibrate_lane_kernel<0>", "sunz_fast_kernel<0, 1>", "nn_source_points_kernel<1>",
+                "DeviceScanInitKernel", "DeviceScanKernel", "nn_target_tables_kernel", "nn_seg_cmax_kernel",
+                "nn_fixed_query_rect_kernel<1>")
 METRICS = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "launch__registers_per_thread", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
@@ -54,12 +55,13 @@ def launches(path, out_prefix):
     total = sum(tot.values())
     lines = [f"ncu --metrics gpu__time_duration.sum --clock-control none ; {BENCH_CMD} (C5, 1 x B200)",
              "per-launch times are cold-cache and serialised: compare SHARES, not absolutes.",
-             "nn_fixed_query_rect_kernel<1> is the fused search+gather of the timed step; <0> (index output) and "
-             "nn_gather_kernel only run in the", "stage micro-benchmarks after the timed region.", ""]
+             "nn_fixed_query_rect_kernel<1> is the fused search+gather of the timed step (plug-in path); <0> (index "
+             "output), the gather, the fused", "calibrate+sunz kernel, bil_sample and fornav only run in the stage "
+             "micro-benchmarks after the timed region.", ""]
     for name, ms in sorted(tot.items(), key=lambda kv: -kv[1]):
         lines.append(f"{ms:10.3f} ms total {cnt[name]:3d} launches {ms / cnt[name]:9.3f} ms/launch {100 * ms / total:5.1f}%  {name[:70]}")
-    step = {n: tot[n] / cnt[n] * (2 if n.startswith("geos_tables") else 1) for n in tot
-            if any(s in n for s in STEP_KERNELS) and "<0>" not in n}
+    step = {n: tot[n] / cnt[n] * (2 if n.startswith("geos_tables") else 1) for n in tot   # sunz + grid build
+            if any(s in n for s in STEP_KERNELS) and not n.startswith("nn_fixed_query_rect_kernel<0>")}
     st = sum(step.values())
     lines += ["", "share of ONE timed step (per-launch times of the kernels a step launches):"]
     for name, ms in sorted(step.items(), key=lambda kv: -kv[1]):
@@ -97,7 +99,7 @@ def report(path, out_prefix, capture_args):
         if rd and wr:
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
             base = kname(r[k])
-            if "<0>" in base:
+            if base.startswith("nn_fixed_query_rect_kernel<0>"):
                 continue  # index-output variant of the stage micro-benchmarks, not part of the timed step
             traffic[base].append(rd[0] * scale[rd[1]] + wr[0] * scale[wr[1]])
     open(out_prefix + "_ncu_final_summary.txt", "w").write("\n".join(lines) + "\n")
@@ -113,7 +115,7 @@ def main():
     ap.add_argument("--round", default="r01")
     ap.add_argument("--launches")
     ap.add_argument("--report")
-    ap.add_argument("--capture-args", default="-k regex:'nn_fixed_query_rect|abi_vis_sunz|nn_source_points|nn_gather' -s 12 -c 5")
+    ap.add_argument("--capture-args", default="-k regex:'nn_fixed_query_rect|sunz_fast|abi_calibrate_lane|nn_source_points|nn_gather_bulk' ...")
     a = ap.parse_args()
     prefix = os.path.join(ROOT, "profiles", a.round)
     if a.launches:
