@@ -333,6 +333,9 @@ int b200_ratio_sharpen_f64(const double *red, const double *green, const double 
 int b200_fill_f32_2d(float *dst, int64_t pitch, int64_t width, int64_t height, float value, void *stream);
 /* the same for `n` rectangles {row0, nrows, col0, ncols} (host array of 4 n int64) of one image, 64 per launch */
 int b200_fill_f32_rects(float *img, int64_t pitch, const int64_t *rects, int32_t n, float value, void *stream);
+/* HOST helper: `value` into a width x height rectangle of a (page-locked) float32 host image with non-temporal stores;
+ * runs on the calling thread (callers split the rows over their own threads).  No device work. */
+int b200_host_fill_f32(float *dst, int64_t pitch, int64_t width, int64_t height, float value);
 int b200_copy_2d(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
                  int64_t width_bytes, int64_t height, void *stream);
 

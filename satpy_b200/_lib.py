@@ -123,6 +123,7 @@ SIGNATURES = {
                                          C.c_int32, C.c_int32, _P]),
     "b200_fill_f32_2d": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_float, _P]),
     "b200_fill_f32_rects": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), C.c_int32, C.c_float, _P]),
+    "b200_host_fill_f32": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_float]),
     "b200_copy_2d": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "b200_bil_info": (C.c_int, [_P, _P, _GEO, C.c_double, C.c_int32, _P, _P, _P, _P, _P]),
     "b200_bil_sample_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_float, _P]),

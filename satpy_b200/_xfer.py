@@ -109,14 +109,25 @@ def fill_async(host3, bands, value):
         _filler = ThreadPoolExecutor(max_workers=nthreads, thread_name_prefix="b200-fill")
     width = host3.shape[-1]
 
+    lib = _lib.load()
+    nb = host3.shape[0]
+    is_f32 = host3.element_size() == 4 and host3.dtype.is_floating_point
+
+    def rect(r0, n, c0, nc):
+        if nc <= 0:
+            return
+        if is_f32:      # non-temporal stores from the library's host helper (ctypes releases the GIL)
+            for b in range(nb):
+                _lib.check(lib.b200_host_fill_f32(host3[b, r0, c0:].data_ptr(), width, nc, n, float(value)))
+        else:
+            host3[:, r0:r0 + n, c0:c0 + nc].fill_(value)
+
     def work(r0, n, c_lo, c_hi):
         if c_hi <= c_lo:
-            host3[:, r0:r0 + n].fill_(value)
+            rect(r0, n, 0, width)
             return
-        if c_lo > 0:
-            host3[:, r0:r0 + n, :c_lo].fill_(value)
-        if c_hi < width:
-            host3[:, r0:r0 + n, c_hi:].fill_(value)
+        rect(r0, n, 0, c_lo)
+        rect(r0, n, c_hi, width - c_hi)
     futures = []
     for r0, n, (c_lo, c_hi) in bands:
         step = max(1, -(-n // nthreads))

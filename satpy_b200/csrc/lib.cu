@@ -202,3 +202,30 @@ extern "C" int b200_fill_f32_rects(float *img, int64_t pitch, const int64_t *rec
     }
     return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// HOST helper (no device work): write `value` into a rectangle of a page-locked float32 image with non-temporal
+// stores.  Results that go back to the host only carry the reachable column spans over PCIe (satpy_b200/_xfer.py); the
+// rest of the image is fill value, written by host threads meanwhile.  Ordinary stores read every cache line before
+// overwriting it (read-for-ownership), which halves the useful memory bandwidth; streaming stores do not.
+#include <emmintrin.h>
+extern "C" int b200_host_fill_f32(float *dst, int64_t pitch, int64_t width, int64_t height, float value) {
+    B200_CHECK_ARG(width >= 0 && height >= 0 && pitch >= width, "bad shape");
+    if (width == 0 || height == 0) return B200_OK;
+    B200_CHECK_ARG(dst != nullptr, "NULL pointer");
+    const __m128 v = _mm_set1_ps(value);
+    for (int64_t r = 0; r < height; ++r) {
+        float *p = dst + r * pitch;
+        int64_t c = 0;
+        while (c < width && (((uintptr_t)(p + c)) & 15)) p[c++] = value;     // head up to a 16-byte boundary
+        for (; c + 16 <= width; c += 16) {
+            _mm_stream_ps(p + c, v);
+            _mm_stream_ps(p + c + 4, v);
+            _mm_stream_ps(p + c + 8, v);
+            _mm_stream_ps(p + c + 12, v);
+        }
+        for (; c < width; ++c) p[c] = value;
+    }
+    _mm_sfence();
+    return B200_OK;
+}

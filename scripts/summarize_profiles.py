@@ -71,15 +71,18 @@ def launches(path, out_prefix):
     print("\n".join(lines))
 
 
-def report(path, out_prefix, capture_args):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, rows = rows[0], rows[1], rows[2:]
-    k = hdr.index("Kernel Name")
+def report(paths, out_prefix, capture_args):
     lines = [f"ncu --set full --clock-control none --import-source on {capture_args}",
              f"{BENCH_CMD} ; C5 full scale, 1 x B200; raw-page metrics per launch", ""]
     traffic = collections.defaultdict(list)
-    for r in rows:
+    all_rows = []
+    for path in paths:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units = rows[0], rows[1]
+        all_rows += [(hdr, units, r) for r in rows[2:]]
+    for hdr, units, r in all_rows:
+        k = hdr.index("Kernel Name")
         lines.append(r[k][:110])
         rd = wr = None
         for m in METRICS:
@@ -114,7 +117,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--round", default="r01")
     ap.add_argument("--launches")
-    ap.add_argument("--report")
+    ap.add_argument("--report", nargs="+")
     ap.add_argument("--capture-args", default="-k regex:'nn_fixed_query_rect|sunz_fast|abi_calibrate_lane|nn_source_points|nn_gather_bulk' ...")
     a = ap.parse_args()
     prefix = os.path.join(ROOT, "profiles", a.round)
