@@ -346,8 +346,6 @@ def run_b200(args):
         nonlocal block_done
         main = torch.cuda.current_stream()
         works = []
-        if exchange == "p2p":
-            peer_image.fill_outside(others, nan)
         for blk in blocks:
             plugin_block(blk, blk.counts_dev, False)
             if block_done is not None:
@@ -369,6 +367,7 @@ def run_b200(args):
         if exchange == "nccl":
             main.wait_stream(comm_stream)
         elif exchange == "p2p":
+            peer_image.fill_outside(others, nan)     # the fill value outside the spans of the other ranks' blocks
             peer_image.finish()
 
     def barrier():

@@ -93,7 +93,26 @@ def source_row_window(src, dst, row0: int, nrows: int, radius: float):
     return first, last - first + 1
 
 
+_SPAN_CACHE: dict = {}
+
+
 def block_column_span(src, dst, row0: int, nrows: int, radius: float, align: int = 32):
+    """Cached front of ``_block_column_span`` (a span depends on the two geometries, the rows and the radius only; the
+    resamplers ask for the same bands scene after scene)."""
+    src, dst = as_geometry(src), as_geometry(dst)
+    try:
+        key = (hash(src), hash(dst), int(row0), int(nrows), float(radius), int(align))
+    except TypeError:
+        return _block_column_span(src, dst, row0, nrows, radius, align)
+    hit = _SPAN_CACHE.get(key)
+    if hit is None:
+        if len(_SPAN_CACHE) > 4096:
+            _SPAN_CACHE.clear()
+        hit = _SPAN_CACHE[key] = _block_column_span(src, dst, row0, nrows, radius, align)
+    return hit
+
+
+def _block_column_span(src, dst, row0: int, nrows: int, radius: float, align: int = 32):
     """Columns ``[c_lo, c_hi)`` of target rows [row0, row0 + nrows) that a geostationary source can reach at all;
     everything outside is fill value whatever the data (the far side of the earth as seen from the satellite).
 
@@ -230,7 +249,9 @@ class PeerImage:
         # thousands of CTAs still to dispatch, a barrier waited 0.5 - 2 ms and the rounds trailed the computation
         # (trace: 12 pushes of 0.47 ms spread over 10.5 ms).  With priority the barrier takes the next slot that frees.
         self.stream = torch.cuda.Stream(priority=-1)
-        self.fill_stream = torch.cuda.Stream(priority=-1)
+        # the fill (one bandwidth-bound launch over everything outside the spans) runs at normal priority: issued after
+        # the last block's search it takes the SM slots that kernel's tail leaves and overlaps the last pushes
+        self.fill_stream = torch.cuda.Stream()
         # "burst" mode (B200_EXCHANGE_MODE=burst; the default from 8 ranks on): one barrier per push, then the copies
         # to all peers at once on their own streams -- every rank sends 1/(N-1) of its egress to every peer and receives
         # the same from each, so the switch is loaded evenly without a barrier per round (28 barriers of ~0.1 ms per

@@ -389,8 +389,11 @@ class B200NearestResampler(_compat.resampler_base()):
 
     def _row_bands(self, nrows, to_host):
         width = self.target_geo_def.width
-        # bands start on 16-byte boundaries of the index / output rows; small results are not worth splitting
-        n = self.ROW_CHUNKS if (to_host and width % 4 == 0 and nrows * width >= (1 << 22)) else 1
+        # bands start on 16-byte boundaries of the index / output rows; a band is worth ~256 MB of result (each costs
+        # three launches and a span computation on the host): 24 for the 12.85 GB of config 5, 2 for an eighth of it
+        n = 1
+        if to_host and width % 4 == 0:
+            n = max(1, min(self.ROW_CHUNKS, (nrows * width * 4) >> 28))
         rows = -(-nrows // max(1, n))
         return [(r0, min(rows, nrows - r0)) for r0 in range(0, nrows, max(1, rows))]
 
