@@ -328,9 +328,15 @@ def run_b200(args):
         """The public flow for one block: reader calibration -> modifier -> resampler (module docstring)."""
         if blk.nrows == 0:
             return None
-        if blk.s_nrows == 0:      # nothing of the source can reach this block
+        if blk.s_nrows == 0:      # nothing of the source can reach this block (beyond 81 degrees of latitude)
             blk.out.fill_(nan)
-            return blk.out.cpu().numpy() if to_host else blk.out
+            if not to_host:
+                return blk.out
+            from satpy_b200 import _xfer           # all fill value: written by the host threads, nothing to copy
+            pin, arr = _xfer.host_empty(blk.out.shape, blk.out.dtype)
+            _xfer.fill_async(pin.reshape(1, *blk.out.shape), [(0, blk.nrows, (0, 0))], nan).result()
+            blk.d2h_bytes = 0
+            return arr
         refl = calibrate_abi(counts_in, cal, "reflectance", device=True)
         ds = DataArrayLite(refl, ("y", "x"), dict(attrs0, area=blk.src_area))
         corrected = sunz([ds])

@@ -99,7 +99,13 @@ def calibrate_abi(counts, cal: ABICalibration, calibration: str = "radiance", ou
         if a.dtype != np.int16:
             raise TypeError(f"ABI counts must be int16/uint16, got {a.dtype}")
         from .. import _xfer
+        import os as _os, time as _time
+        _t0 = _time.perf_counter()
         t = _xfer.to_device(a)
+        if _os.environ.get("B200_XFER_TRACE") and _os.environ.get("RANK", "0") == "0":
+            import sys as _sys
+            torch.cuda.synchronize()
+            print(f"[xfer] H2D {a.nbytes / 1e6:.0f} MB in {1e3 * (_time.perf_counter() - _t0):.1f} ms", file=_sys.stderr)
     else:
         t = counts.contiguous()
         if t.dtype != torch.int16:

@@ -504,6 +504,9 @@ class B200NearestResampler(_compat.resampler_base()):
         torch = _lib.require_cuda()
         lib = _lib.load()
         src, dst = self.source_geo_def, self.target_geo_def
+        import os as _os, time as _time
+        _tr = _os.environ.get("B200_XFER_TRACE") and _os.environ.get("RANK", "0") == "0"
+        _t0 = _time.perf_counter()
         t, was_numpy = self._as_device(torch, arr)
         if t.dtype != torch.float32:
             raise TypeError("fused resampling works on float32 data")
@@ -531,9 +534,11 @@ class B200NearestResampler(_compat.resampler_base()):
             ev[1].record()
         host_arr = None
         bands = [(r0, n, (0, width)) for r0, n in self._row_bands(nrows, False)]
+        _t1 = _time.perf_counter()
         if to_host:
             host_t, host_arr, h3, bands, fut = self._host_plan(torch, out, row0, nrows, radius, float(fill_value))
             cs = _xfer.copy_stream()
+        _t2 = _time.perf_counter()
         out3 = out.reshape(nbands, nrows, width)
         stream = _lib.stream_ptr(torch)
         for r0, n, span in bands:
@@ -548,10 +553,17 @@ class B200NearestResampler(_compat.resampler_base()):
             tr.append(("build", ev[0], ev[1]))
             tr.append(("query_gather", ev[1], ev[2]))
         del grid   # stream-ordered: freed after the queries queued above
+        _t3 = _time.perf_counter()
         if to_host:
             out.record_stream(cs)
             cs.synchronize()
+            _t4 = _time.perf_counter()
             fut.result()
+            if _tr:
+                import sys as _sys
+                print(f"[xfer] rows {nrows}: grid {1e3 * (_t1 - _t0):.1f} ms, host plan {1e3 * (_t2 - _t1):.1f} ms, launches "
+                      f"{1e3 * (_t3 - _t2):.1f} ms, wait copies {1e3 * (_t4 - _t3):.1f} ms, wait fill "
+                      f"{1e3 * (_time.perf_counter() - _t4):.1f} ms, bands {len(bands)}", file=_sys.stderr)
         return self._finish(data, out, host_arr)
 
     def resample_fused(self, data, radius_of_influence, fill_value=np.nan, row_window=None, out=None,
