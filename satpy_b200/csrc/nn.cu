@@ -833,7 +833,7 @@ static void launch_gather(const void *data, void *out, const int32_t *gidx, int6
                                                                    src_band_stride, dst_band_stride, f);
 }
 
-// Bulk-staged variant (float32 / 4-byte elements, one band): the index stream comes in and the result goes out through
+// Bulk-staged variant (4-byte elements, any number of bands): the index stream comes in and the result goes out through
 // shared memory with cp.async.bulk (b200_bulk.cuh), GATHER_STAGES tiles in flight per CTA; threads only issue the
 // scattered source loads.  A/B against the direct kernel in scripts/variant_bench.py.
 #define GATHER_TILE 2048
@@ -845,7 +845,7 @@ struct __align__(128) GatherStage {
 
 __global__ void __launch_bounds__(256)
 nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ out, const int32_t *__restrict__ gidx,
-                      int64_t n_tiles, uint32_t fill) {
+                      int64_t n_tiles, uint32_t fill, int nbands, int64_t src_band_stride, int64_t dst_band_stride) {
     extern __shared__ __align__(128) unsigned char gather_smem[];
     GatherStage *stage = reinterpret_cast<GatherStage *>(gather_smem);
     __shared__ uint64_t full[GATHER_STAGES];
@@ -869,25 +869,35 @@ nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ 
     uint32_t phase = 0;
     for (int64_t tile = first; tile < n_tiles; tile += step) {
         mbar_wait(&full[s], phase);
-        if (t == 0) bulk_wait_read<GATHER_STAGES - 1>();
-        __syncthreads();
+        for (int b = 0; b < nbands; ++b) {
+            // the bulk store that last read stage[s].out must have finished reading it: the one GATHER_STAGES tiles ago
+            // for the first band, the previous band's for the others (one output tile per stage serves every band)
+            if (t == 0) {
+                if (b == 0) bulk_wait_read<GATHER_STAGES - 1>();
+                else bulk_wait_read<0>();
+            }
+            __syncthreads();
+            const uint32_t *src = data + (int64_t)b * src_band_stride;
 #pragma unroll
-        for (int j = 0; j < GATHER_TILE / 1024; ++j) {
-            const int4 ix = *reinterpret_cast<const int4 *>(stage[s].idx + j * 1024 + 4 * t);
-            uint4 v;
-            v.x = ix.x < 0 ? fill : __ldg(data + ix.x);
-            v.y = ix.y < 0 ? fill : __ldg(data + ix.y);
-            v.z = ix.z < 0 ? fill : __ldg(data + ix.z);
-            v.w = ix.w < 0 ? fill : __ldg(data + ix.w);
-            *reinterpret_cast<uint4 *>(stage[s].out + j * 1024 + 4 * t) = v;
+            for (int j = 0; j < GATHER_TILE / 1024; ++j) {
+                const int4 ix = *reinterpret_cast<const int4 *>(stage[s].idx + j * 1024 + 4 * t);
+                uint4 v;
+                v.x = ix.x < 0 ? fill : __ldg(src + ix.x);
+                v.y = ix.y < 0 ? fill : __ldg(src + ix.y);
+                v.z = ix.z < 0 ? fill : __ldg(src + ix.z);
+                v.w = ix.w < 0 ? fill : __ldg(src + ix.w);
+                *reinterpret_cast<uint4 *>(stage[s].out + j * 1024 + 4 * t) = v;
+            }
+            bulk_fence_smem_writes();
+            __syncthreads();
+            if (t == 0) {
+                bulk_s2g(out + (int64_t)b * dst_band_stride + tile * GATHER_TILE, stage[s].out, GATHER_TILE * 4);
+                bulk_commit();
+            }
         }
-        bulk_fence_smem_writes();
-        __syncthreads();
         if (t == 0) {
-            bulk_s2g(out + tile * GATHER_TILE, stage[s].out, GATHER_TILE * 4);
-            bulk_commit();
             const int64_t next = tile + (int64_t)GATHER_STAGES * step;
-            if (next < n_tiles) {
+            if (next < n_tiles) {   // every thread has read stage[s].idx for the last band (barrier above)
                 mbar_expect_tx(&full[s], GATHER_TILE * 4);
                 bulk_g2s(stage[s].idx, gidx + next * GATHER_TILE, GATHER_TILE * 4, &full[s]);
             }
@@ -937,7 +947,8 @@ extern "C" int b200_nn_gather_variant(const void *data, void *out, const int32_t
     B200_CHECK_ARG(nbands == 1 || dst_band_stride >= n_out, "band stride smaller than one image");
     cudaStream_t s = (cudaStream_t)stream;
     int64_t done = 0;
-    if (variant == 1 && elem_size == 4 && nbands == 1 && (((uintptr_t)out) & 15) == 0 && n_out >= GATHER_TILE) {
+    if (variant == 1 && elem_size == 4 && (nbands == 1 || (dst_band_stride & 3) == 0) && (((uintptr_t)out) & 15) == 0 &&
+        n_out >= GATHER_TILE) {
         // whole tiles through the bulk-staged kernel, the rest (< one tile) through the direct one
         const int64_t n_tiles = n_out / GATHER_TILE;
         const size_t smem = sizeof(GatherStage) * GATHER_STAGES + 128;
@@ -951,7 +962,7 @@ extern "C" int b200_nn_gather_variant(const void *data, void *out, const int32_t
         uint32_t f;
         memcpy(&f, fill, 4);
         nn_gather_bulk_kernel<<<(int)grid, 256, smem, s>>>(static_cast<const uint32_t *>(data), static_cast<uint32_t *>(out),
-                                                         gather_index, n_tiles, f);
+                                                         gather_index, n_tiles, f, nbands, src_band_stride, dst_band_stride);
         B200_LAUNCH_CHECK();
         done = n_tiles * GATHER_TILE;
         if (done == n_out) return B200_OK;

@@ -24,6 +24,8 @@
 // target rows: the source records they share then stay in L2 although per-item cost varies 10x (on/off disk).
 #include "nn_common.cuh"
 #include "b200_geos_fast.cuh"
+#include "b200_bulk.cuh"
+#include <stdlib.h>
 
 #define GEOS_BOUND_FACTOR 0.975
 
@@ -1016,6 +1018,80 @@ bil_sample_f32_kernel(const float *__restrict__ data, float *__restrict__ out, c
     }
 }
 
+// Bulk-staged variant (one band): the three input streams (4 corner indices, t, s: 32 B per output) come in through
+// shared memory with cp.async.bulk + mbarrier, three tiles in flight per CTA, the result goes out the same way; the
+// threads only issue the four scattered source loads.  Same structure as nn_gather_bulk_kernel (nn.cu).
+#define BIL_TILE 1024
+#define BIL_STAGES 3
+struct __align__(128) BilStage {
+    int32_t idx[4 * BIL_TILE];
+    double t[BIL_TILE];
+    double s[BIL_TILE];
+    float out[BIL_TILE];
+};
+
+__global__ void __launch_bounds__(256)
+bil_sample_bulk_kernel(const float *__restrict__ data, float *__restrict__ out, const int32_t *__restrict__ gidx,
+                       const double *__restrict__ tt_, const double *__restrict__ ss_, int64_t n_tiles, float fill) {
+    extern __shared__ __align__(128) unsigned char bil_smem[];
+    BilStage *stage = reinterpret_cast<BilStage *>(bil_smem);
+    __shared__ uint64_t full[BIL_STAGES];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int k = 0; k < BIL_STAGES; ++k) mbar_init(&full[k], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    const uint32_t in_bytes = BIL_TILE * (16 + 8 + 8);
+    auto load_tile = [&](int k, int64_t tile) {
+        mbar_expect_tx(&full[k], in_bytes);
+        bulk_g2s(stage[k].idx, gidx + tile * 4 * BIL_TILE, BIL_TILE * 16, &full[k]);
+        bulk_g2s(stage[k].t, tt_ + tile * BIL_TILE, BIL_TILE * 8, &full[k]);
+        bulk_g2s(stage[k].s, ss_ + tile * BIL_TILE, BIL_TILE * 8, &full[k]);
+    };
+    if (t == 0)
+        for (int k = 0; k < BIL_STAGES; ++k)
+            if (first + (int64_t)k * step < n_tiles) load_tile(k, first + (int64_t)k * step);
+    int k = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += step) {
+        mbar_wait(&full[k], phase);
+        if (t == 0) bulk_wait_read<BIL_STAGES - 1>();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < BIL_TILE / 256; ++j) {
+            const int o = j * 256 + t;
+            const int4 ix = *reinterpret_cast<const int4 *>(stage[k].idx + 4 * o);
+            const double tt = stage[k].t[o], ss = stage[k].s[o];
+            float v = fill;
+            if (ix.x >= 0 && ix.y >= 0 && ix.z >= 0 && ix.w >= 0) {
+                // ((p1 * (1-s)) * (1-t)) ... in the reference's order of operations (as bil_sample_f32_kernel)
+                double r1 = (double)__ldg(data + ix.x) * (1.0 - ss) * (1.0 - tt);
+                double r2 = (double)__ldg(data + ix.y) * ss * (1.0 - tt);
+                double r3 = (double)__ldg(data + ix.z) * (1.0 - ss) * tt;
+                double r4 = (double)__ldg(data + ix.w) * ss * tt;
+                double res = ((r1 + r2) + r3) + r4;
+                v = isnan(res) ? fill : (float)res;
+            }
+            stage[k].out[o] = v;
+        }
+        bulk_fence_smem_writes();
+        __syncthreads();
+        if (t == 0) {
+            bulk_s2g(out + tile * BIL_TILE, stage[k].out, BIL_TILE * 4);
+            bulk_commit();
+            const int64_t next = tile + (int64_t)BIL_STAGES * step;
+            if (next < n_tiles) load_tile(k, next);
+        }
+        if (++k == BIL_STAGES) {
+            k = 0;
+            phase ^= 1;
+        }
+    }
+    if (t == 0) bulk_wait_all();
+}
+
 extern "C" int b200_bil_sample_f32(const float *data, float *out, const int32_t *gather_index, const double *t,
                                    const double *s, int64_t n_out, int32_t nbands, int64_t src_band_stride,
                                    int64_t dst_band_stride, float fill, void *stream) {
@@ -1024,8 +1100,30 @@ extern "C" int b200_bil_sample_f32(const float *data, float *out, const int32_t 
     B200_CHECK_ARG(data && out && gather_index && t && s, "NULL pointer");
     B200_CHECK_ARG(((uintptr_t)gather_index & 15) == 0, "gather_index must be 16-byte aligned");
     B200_CHECK_ARG(nbands == 1 || dst_band_stride >= n_out, "band stride smaller than one image");
-    bil_sample_f32_kernel<<<b200_grid_for(n_out, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        data, out, gather_index, t, s, n_out, nbands, src_band_stride, dst_band_stride, fill);
+    int64_t done = 0;
+    static int variant = -1;   // B200_BIL_VARIANT: 0 direct, 1 bulk-staged (default)
+    if (variant < 0) {
+        const char *e = getenv("B200_BIL_VARIANT");
+        variant = e ? (atoi(e) != 0) : 1;
+    }
+    const bool aligned = ((((uintptr_t)out) | ((uintptr_t)t) | ((uintptr_t)s)) & 15) == 0;
+    if (variant == 1 && nbands == 1 && aligned && n_out >= BIL_TILE) {
+        const int64_t n_tiles = n_out / BIL_TILE;
+        const size_t smem = sizeof(BilStage) * BIL_STAGES + 128;
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200_CUDA(cudaFuncSetAttribute(bil_sample_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        int64_t grid = (int64_t)B200_NUM_SMS * 2;
+        if (grid > n_tiles) grid = n_tiles;
+        bil_sample_bulk_kernel<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(data, out, gather_index, t, s, n_tiles, fill);
+        B200_LAUNCH_CHECK();
+        done = n_tiles * BIL_TILE;
+        if (done == n_out) return B200_OK;
+    }
+    bil_sample_f32_kernel<<<b200_grid_for(n_out - done, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        data, out + done, gather_index + 4 * done, t + done, s + done, n_out - done, nbands, src_band_stride, dst_band_stride, fill);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -89,6 +89,32 @@ def main():
                   "frac_of_measured_hbm": round(nbytes / ms / 1e6 / pk, 3), "identical_to_variant_0": same}
             rows.append(rr)
             print(json.dumps(rr), flush=True)
+        # config 2: three bands through one index stream (5424^2 -> 9050^2)
+        del r, gi, res, data
+        torch.cuda.empty_cache()
+        s2, d2 = demo.make_area("goes_east_abi_f_2km"), demo.make_area("goes_east_eqc_2km")
+        r2 = B200NearestResampler(s2, d2)
+        r2.precompute(radius_of_influence=5000.0, gather_only=True)
+        gi2 = r2._current["gather_index"]
+        rgb = torch.rand((3,) + s2.shape, device="cuda")
+        res2 = torch.empty((3,) + d2.shape, dtype=torch.float32, device="cuda")
+        first = None
+        for variant in (0, 1):
+            def run():
+                _lib.check(lib.b200_nn_gather_variant(rgb.data_ptr(), res2.data_ptr(), gi2.data_ptr(), gi2.numel(), 3, s2.size,
+                                                      gi2.numel(), 4, C.cast(fill, C.c_void_p), variant, stream))
+            ms = timeit(run, steps=10)
+            same = None
+            if variant == 0:
+                first = res2.clone()
+            else:
+                same = bool(((res2 == first) | (torch.isnan(res2) & torch.isnan(first))).all())
+            nbytes = (4 + 3 * 4) * d2.size + 3 * 4 * int(np.pi / 4 * s2.size)
+            rr = {"kernel": "nn_gather x3 bands (config 2)", "variant": variant, "ms": round(ms, 4),
+                  "gbs": round(nbytes / ms / 1e6, 1), "frac_of_measured_hbm": round(nbytes / ms / 1e6 / pk, 3),
+                  "identical_to_variant_0": same}
+            rows.append(rr)
+            print(json.dumps(rr), flush=True)
     if args.out:
         json.dump(rows, open(args.out, "w"), indent=1)
 

@@ -121,3 +121,17 @@ def test_calibration_and_gather_variants_are_bit_identical(n):
     np.testing.assert_array_equal(res[1], res[0])
     exp = np.where(gi.cpu().numpy() < 0, np.nan, data.cpu().numpy()[np.maximum(gi.cpu().numpy(), 0)])
     np.testing.assert_array_equal(res[0], exp.astype(np.float32))
+    # three bands through one index stream (band strides that keep 16-byte alignment, and one that does not)
+    data3 = torch.from_numpy(rng.uniform(0, 100, size=(3, n_src)).astype(np.float32)).cuda()
+    for pad in (0, 4, 2):
+        stride = n + pad
+        res3 = []
+        for variant in (0, 1):
+            out = torch.full((3 * stride,), -3.0, dtype=torch.float32, device="cuda")
+            _lib.check(lib.b200_nn_gather_variant(data3.data_ptr(), out.data_ptr(), gi.data_ptr(), n, 3, n_src, stride, 4,
+                                                  C.cast(fill, C.c_void_p), variant, stream))
+            res3.append(out.cpu().numpy())
+        np.testing.assert_array_equal(res3[1], res3[0])
+        for b in range(3):
+            e = np.where(gi.cpu().numpy() < 0, np.nan, data3[b].cpu().numpy()[np.maximum(gi.cpu().numpy(), 0)])
+            np.testing.assert_array_equal(res3[0][b * stride: b * stride + n], e.astype(np.float32))

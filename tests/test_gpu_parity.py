@@ -369,6 +369,49 @@ def test_nearest_engines_agree_exactly(dname, dscale, radius):
     assert 0.0 < hit < 1.0
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_engines_agree_on_random_limb_crossing_cases(seed):
+    """The lattice-model pruning of ``fixed_grid`` rests on empirically fitted margins, so it is held to the strict mode
+    and to the bucket engine on randomised cases: both sweeps (ABI x, SEVIRI y), source pixels of 8-40 km, radii from 1
+    to 50 source pixels, random masks plus a masked rectangle, source row windows, and eqc / laea target patches
+    placed across the limb."""
+    import math
+    import torch
+    rng = np.random.default_rng(100 + seed)
+    sname, lon0 = (("goes_east_abi_f_2km", -75.0) if seed % 2 == 0 else ("msg_seviri_fes_3km", 0.0))
+    nsrc = int(rng.integers(280, 700))
+    src = demo.make_area(sname, nsrc / demo.AREAS[sname][1])
+    pix = (src.area_extent[2] - src.area_extent[0]) / src.width
+    if rng.random() < 0.4:                               # a band of source rows (what a multi-GPU block sees)
+        r0 = int(rng.integers(0, src.height // 3))
+        src = src.row_window(r0, int(rng.integers(src.height // 3, src.height - r0)))
+    radius = float(pix * rng.choice([1.0, 1.7, 3.0, 6.0, 12.0, 25.0, 50.0]))
+    clon = lon0 + float(rng.choice([-1, 1])) * float(rng.uniform(45.0, 84.0))     # across the east / west limb
+    clat = float(rng.uniform(-75.0, 75.0))
+    tpix = pix * float(rng.uniform(0.3, 1.5))
+    w, h = int(rng.integers(150, 380)), int(rng.integers(120, 300))
+    if seed % 3 == 0:
+        proj = {"proj": "laea", "lat_0": clat, "lon_0": clon, "ellps": "WGS84"}
+        ext = (-w * tpix / 2, -h * tpix / 2, w * tpix / 2, h * tpix / 2)
+    else:
+        a = 6378137.0
+        x0, y0 = math.radians(clon) * a, math.radians(clat) * a
+        proj = {"proj": "eqc", "lon_0": 0.0, "ellps": "WGS84"}
+        ext = (x0 - w * tpix / 2, y0 - h * tpix / 2, x0 + w * tpix / 2, y0 + h * tpix / 2)
+    dst = AreaDefinition("t", "t", "t", proj, w, h, ext)
+    mask = rng.random(src.shape) < 0.05
+    mr, mc = int(rng.integers(0, src.height - 20)), int(rng.integers(0, src.width - 20))
+    mask[mr:mr + 20, mc:mc + 20] = True
+    out = {}
+    for method in ("bucket", "fixed_grid", "fixed_grid_strict"):
+        r = B200NearestResampler(src, dst)
+        r.precompute(radius_of_influence=radius, method=method, mask=mask)
+        out[method] = r._current["gather_index"].clone()
+        np.testing.assert_array_equal(r._current["valid_input_index"].cpu().numpy().astype(bool) & mask, False)
+    assert bool(torch.equal(out["fixed_grid"], out["fixed_grid_strict"])), "pruned != strict"
+    assert bool(torch.equal(out["bucket"], out["fixed_grid_strict"])), "bucket != fixed grid"
+
+
 def test_fixed_grid_pruning_is_exact_on_the_full_disk():
     """The lattice-model pruning of the fixed-grid search against its strict mode over a whole (coarse) full disk seen
     from a fine global grid -- nadir, mid-latitudes and the limb, where pixels stretch to many times their nadir size --
