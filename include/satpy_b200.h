@@ -248,10 +248,18 @@ int b200_nn_grid_create(const b200_geo_t *src, const uint8_t *mask, double radiu
 /* Same, choosing the search engine: 0 = automatic, 1 = bucket grid (any source), 2 = fixed grid
  * (geostationary area sources only: the source lattice itself is the index, see csrc/nn_geos.cu;
  * B200_EUNSUPPORTED for other sources), 3 = fixed grid in strict mode (every lattice point of the
- * rigorous search disc is examined; 2 rules most of them out with a local lattice model first).
+ * rigorous search disc is examined by the general loop; 2 settles radii of a few source pixels with
+ * fixed 2x2 / 4x4 stencils and a satellite-distance-corrected bound first).
  * All engines return identical indices.
  * `n_valid` may be NULL: the fixed-grid engine then builds without synchronising the stream (the
- * count is read back by b200_nn_grid_n_valid when somebody asks); the bucket engine always needs it. */
+ * count is read back by b200_nn_grid_n_valid when somebody asks); the bucket engine always needs it.
+ * B200_NN_LIGHT may be OR-ed into `method`: when the fixed-grid engine serves the source, no mask
+ * is given and n_valid is NULL, the structure keeps float32 points only (16 instead of 52 bytes per
+ * source pixel; the rare exact float64 decisions recompute their candidates from the projection).
+ * Such a structure serves b200_nn_query_gather_f32 and b200_nn_query with gather_index /
+ * valid_output; b200_nn_query(index_array), b200_nn_grid_n_valid and b200_bil_info return
+ * B200_EUNSUPPORTED for it.  The flag is ignored where the conditions do not hold. */
+#define B200_NN_LIGHT 0x100
 int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask, double radius,
                            uint8_t *valid_input, int64_t *n_valid /* host, may be NULL */,
                            b200_nn_grid_t **grid /* host out */, int32_t method, void *stream);

@@ -99,9 +99,11 @@ nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restr
             if (ok) b200_lonlat2xyz(lon, lat, x, y, z, lam, phi);
         }
         valid_input[i] = ok ? 1 : 0;
-        double2 *p = reinterpret_cast<double2 *>(rec + i);
-        p[0] = make_double2(x, y);
-        p[1] = make_double2(z, __longlong_as_double((long long)i));
+        if (rec) {
+            double2 *p = reinterpret_cast<double2 *>(rec + i);
+            p[0] = make_double2(x, y);
+            p[1] = make_double2(z, __longlong_as_double((long long)i));
+        }
         if (rec32) rec32[i] = ok ? make_float4((float)x, (float)y, (float)z, 0.0f)
                                  : make_float4(__int_as_float(0x7f800000), 0.0f, 0.0f, 0.0f);
         if (cell_of) cell_of[i] = ok ? b200_cell_of(band_off, lam, phi, phi0, inv_dphi, nbands) : -1;
@@ -329,7 +331,7 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
         NN_TRY(cudaStreamSynchronize(s));  // h_off is pageable: finish before freeing it
         NN_TRY(cudaMallocAsync((void **)&cell_of, (size_t)n_src * sizeof(int32_t), s));
     }
-    NN_TRY(cudaMallocAsync((void **)&rec, (size_t)n_src * sizeof(double4), s));
+    if (!g->light) NN_TRY(cudaMallocAsync((void **)&rec, (size_t)n_src * sizeof(double4), s));
     if (!bucket) NN_TRY(cudaMallocAsync((void **)&g->pts32, (size_t)n_src * sizeof(float4), s));
     rc = b200_geos_fast_prepare(src, &fast, s);
     if (rc) goto fail;
@@ -341,6 +343,12 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
             S, mask, valid_input, rec, g->pts32, cell_of, g->band_off, phi0, inv_dphi, nbands, fast);
     NN_TRY(cudaGetLastError());
     b200_geos_fast_release(&fast, s);
+    if (g->light) {   // fused path: no compressed indices are ever asked for -- no prefix table, no count
+        g->valid_input = valid_input;
+        g->n_valid = -1;
+        g->nbytes = n_src * (int64_t)sizeof(float4);
+        goto fail;  // (common clean-up)
+    }
     rc = nn_prefix(g, valid_input, s, lazy_count && !bucket);
     if (rc) goto fail;
     if (!bucket) {
@@ -383,6 +391,8 @@ extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask
     B200_CHECK_ARG(grid != nullptr, "NULL output argument");
     B200_CHECK_ARG(valid_input != nullptr, "valid_input is NULL");
     B200_CHECK_ARG(radius > 0.0 && isfinite(radius), "radius_of_influence must be positive and finite");
+    const bool want_light = (method & B200_NN_LIGHT) != 0;
+    method &= ~B200_NN_LIGHT;
     B200_CHECK_ARG(method >= 0 && method <= 3, "method must be 0 (auto), 1 (bucket), 2 (fixed grid) or 3 (fixed grid, strict)");
     // the structure covers the source row window [row0, row0 + nrows); indices are relative to its first pixel
     const int64_t n_src = src->nrows * src->width;
@@ -403,6 +413,9 @@ extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask
     memset(g, 0, sizeof(*g));
     g->mode = (method == 0) ? (fixed_ok ? B200_NN_FIXED_GRID : B200_NN_BUCKET) : method;
     g->strict = strict;
+    // light: only the fixed-grid engine, only without a mask (an off-disk test cannot reproduce a mask), only when the
+    // caller does not want the count now
+    g->light = want_light && g->mode == B200_NN_FIXED_GRID && mask == nullptr && n_valid == nullptr;
     g->n_src = n_src;
     g->radius = radius;
     g->src = *src;
@@ -423,6 +436,10 @@ extern "C" int b200_nn_grid_create_ex(const b200_geo_t *src, const uint8_t *mask
 
 extern "C" int b200_nn_grid_n_valid(b200_nn_grid_t *grid, int64_t *n_valid) {
     B200_CHECK_ARG(grid != nullptr && n_valid != nullptr, "NULL argument");
+    if (grid->n_valid < 0 && grid->light) {
+        b200_set_error("b200_nn_grid_n_valid: a light search structure keeps no count");
+        return B200_EUNSUPPORTED;
+    }
     if (grid->n_valid < 0) {  // built lazily: read the last prefix entry + the last mask byte back now
         int32_t last_prefix = 0;
         uint8_t last_valid = 0;
@@ -606,6 +623,8 @@ nn_target_tables_kernel(const __grid_constant__ TableArg A, TgtCol *__restrict__
             double rel = b200_adjlon(c.lam - A.lam0);
             c.s_rel = (float)sin(rel);
             c.c_rel = (float)cos(rel);
+            // an invalid column fails every visibility test (rc * c_rel >= vis_min) without its flag being read
+            if (!c.valid) c.c_rel = __int_as_float(0x7fc00000);
             c.pad = 0;
             c.pad2 = 0.0;
             cols[i] = c;
@@ -843,9 +862,12 @@ struct __align__(128) GatherStage {
     uint32_t out[GATHER_TILE];
 };
 
+// MULTI = false: one band, compiled without the band loop (the single-band kernel lost 9 % when the loop was added)
+template <bool MULTI>
 __global__ void __launch_bounds__(256)
 nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ out, const int32_t *__restrict__ gidx,
-                      int64_t n_tiles, uint32_t fill, int nbands, int64_t src_band_stride, int64_t dst_band_stride) {
+                      int64_t n_tiles, uint32_t fill, int nbands_, int64_t src_band_stride, int64_t dst_band_stride) {
+    const int nbands = MULTI ? nbands_ : 1;
     extern __shared__ __align__(128) unsigned char gather_smem[];
     GatherStage *stage = reinterpret_cast<GatherStage *>(gather_smem);
     __shared__ uint64_t full[GATHER_STAGES];
@@ -869,6 +891,7 @@ nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ 
     uint32_t phase = 0;
     for (int64_t tile = first; tile < n_tiles; tile += step) {
         mbar_wait(&full[s], phase);
+#pragma unroll 1
         for (int b = 0; b < nbands; ++b) {
             // the bulk store that last read stage[s].out must have finished reading it: the one GATHER_STAGES tiles ago
             // for the first band, the previous band's for the others (one output tile per stage serves every band)
@@ -877,7 +900,7 @@ nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ 
                 else bulk_wait_read<0>();
             }
             __syncthreads();
-            const uint32_t *src = data + (int64_t)b * src_band_stride;
+            const uint32_t *src = MULTI ? data + (int64_t)b * src_band_stride : data;
 #pragma unroll
             for (int j = 0; j < GATHER_TILE / 1024; ++j) {
                 const int4 ix = *reinterpret_cast<const int4 *>(stage[s].idx + j * 1024 + 4 * t);
@@ -891,7 +914,7 @@ nn_gather_bulk_kernel(const uint32_t *__restrict__ data, uint32_t *__restrict__ 
             bulk_fence_smem_writes();
             __syncthreads();
             if (t == 0) {
-                bulk_s2g(out + (int64_t)b * dst_band_stride + tile * GATHER_TILE, stage[s].out, GATHER_TILE * 4);
+                bulk_s2g((MULTI ? out + (int64_t)b * dst_band_stride : out) + tile * GATHER_TILE, stage[s].out, GATHER_TILE * 4);
                 bulk_commit();
             }
         }
@@ -954,15 +977,20 @@ extern "C" int b200_nn_gather_variant(const void *data, void *out, const int32_t
         const size_t smem = sizeof(GatherStage) * GATHER_STAGES + 128;
         static bool attr_set = false;
         if (!attr_set) {
-            B200_CUDA(cudaFuncSetAttribute(nn_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CUDA(cudaFuncSetAttribute(nn_gather_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CUDA(cudaFuncSetAttribute(nn_gather_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
         int64_t grid = (int64_t)B200_NUM_SMS * 4;
         if (grid > n_tiles) grid = n_tiles;
         uint32_t f;
         memcpy(&f, fill, 4);
-        nn_gather_bulk_kernel<<<(int)grid, 256, smem, s>>>(static_cast<const uint32_t *>(data), static_cast<uint32_t *>(out),
-                                                         gather_index, n_tiles, f, nbands, src_band_stride, dst_band_stride);
+        if (nbands == 1)
+            nn_gather_bulk_kernel<false><<<(int)grid, 256, smem, s>>>(static_cast<const uint32_t *>(data), static_cast<uint32_t *>(out),
+                                                                    gather_index, n_tiles, f, 1, 0, 0);
+        else
+            nn_gather_bulk_kernel<true><<<(int)grid, 256, smem, s>>>(static_cast<const uint32_t *>(data), static_cast<uint32_t *>(out),
+                                                                   gather_index, n_tiles, f, nbands, src_band_stride, dst_band_stride);
         B200_LAUNCH_CHECK();
         done = n_tiles * GATHER_TILE;
         if (done == n_out) return B200_OK;

@@ -9,6 +9,7 @@
 #define B200_NN_BUCKET 1
 #define B200_NN_FIXED_GRID 2
 #define B200_NN_FIXED_GRID_STRICT 3  /* request only: a fixed-grid structure with strict = 1 */
+/* B200_NN_LIGHT (request flag, include/satpy_b200.h): light structure when the fixed-grid engine serves the source */
 
 int b200_check_geo(const b200_geo_t *geo, const char *who);
 
@@ -16,6 +17,7 @@ int b200_check_geo(const b200_geo_t *geo, const char *who);
 struct b200_nn_grid {
     int mode;  // B200_NN_BUCKET or B200_NN_FIXED_GRID
     int strict;  // fixed grid: examine every point of the rigorous disc (no lattice-model pruning)
+    int light;   // fixed grid, built for the fused path: float32 points only (no float64 records, no prefix table)
     int device;
     void *stream;  // the stream the structure was built on; its memory is stream-ordered on it
     int64_t n_src, n_valid;
@@ -39,19 +41,24 @@ struct b200_nn_grid {
 
 // Per-column / per-row quantities of a target whose lon depends on the column only and whose lat depends on the row
 // only (longlat, eqc, merc): every transcendental of the query is evaluated W + H times instead of W * H times.
-struct TgtCol {  // 48 B
-    double lam, sin_lam, cos_lam;  // radians; sin/cos exactly as b200_lonlat2xyz computes them
-    float s_rel, c_rel;            // sin/cos(lam - lam0 of a geos source), float32 (fixed-grid mode)
+// Field order: what the fixed-grid kernel reads per pixel sits in aligned 16-byte groups (one 128-bit load each).
+struct __align__(16) TgtCol {  // 48 B
+    double sin_lam, cos_lam;       // exactly as b200_lonlat2xyz computes them                        [one 128-bit load]
+    double lam;                    // radians
+    float s_rel, c_rel;            // sin/cos(lam - lam0 of a geos source), float32 (fixed-grid mode); c_rel = NaN for
+                                   // an invalid column
     int32_t valid, pad;
     double pad2;
 };
-struct TgtRow {  // 64 B
-    double phi, sin_phi, cos_phi;
+struct __align__(16) TgtRow {  // 64 B
+    double phi, sin_phi;
+    double cos_phi;
+    double dlam1;      // bucket mode, first phase: longitude half-width of the one-cell cap
     double dlam;       // longitude half-width of the search cap at this latitude (bucket mode); >= pi: whole circle
     float rc, rs;      // geos source: r*cos(pg), r*sin(pg) of the geocentric latitude (fixed-grid mode)
+                       //                                              [dlam, rc, rs: one 128-bit load]
     int32_t valid, b_lo, b_hi;
     int32_t b_1;       // bucket mode, first phase (one-cell cap): b_lo1 | (b_hi1 - b_lo1) << 24
-    double dlam1;      // ... and its longitude half-width
 };
 
 // lon depends on the column only and lat on the row only

@@ -67,6 +67,8 @@ int b200_nn_fixed_grid_supported(const b200_geo_t *src) {
 }
 
 struct GeosDev {
+    GeosFast fast;         // light structures (pts == NULL): projection tables, the exact path recomputes float64 points
+    int64_t src_row0;      // first row of the source window in the area (for `fast`)
     const double4 *pts;
     const float4 *pts32;   // float32 copy of the points (pre-filter)
     const int32_t *prefix;
@@ -81,6 +83,8 @@ struct GeosDev {
     float inv_step;                 // 1 / (0.975 * min pixel size)
     float radius_f;                 // radius of influence
     float r2_slack;                 // (radius + GEOS_F32_SLACK)^2 * (1 + eps)
+    float k_a, k_b, k_cap;          // satellite-distance factor of the tiered search: min(k_cap, k_a * rho^2 + k_b)
+    int32_t Wm3, Hm3;               // max(0, W - 3), max(0, H - 3): blocks whose 4 x 4 window lies inside the grid
     double r2;
 };
 
@@ -109,6 +113,26 @@ __device__ __forceinline__ float nn_d2f(const float4 &p, float tx, float ty, flo
 __device__ __forceinline__ float nn_block_clearance(float fc, float fr, int c0, int r0) {
     const float fx = fc - (float)c0, fy = fr - (float)r0;
     return 1.0f + fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy));
+}
+
+// One candidate of the exact search.  Full structures read its float64 record; LIGHT structures (built for the fused
+// path: float32 points only, 17 instead of 53 bytes written per source pixel) recompute the point from the projection
+// tables with the function that would have produced the record (geos_fast_xyz), for the 0.3 % of the targets that get
+// here.  An off-disk pixel has no point and loses, like the NaN of its record.
+__device__ __forceinline__ void nn_exact_consider(const GeosDev &G, long long idx, double tx, double ty, double tz,
+                                                  Best &best) {
+    if (G.pts) {
+        b200_nn_consider(G.pts + idx, tx, ty, tz, best);
+        return;
+    }
+    const long long r = idx / G.W;
+    double x, y, z, sl, cl, sp, cp;
+    if (!geos_fast_xyz(G.fast, G.src_row0 + r, idx - r * G.W, B200_R_EARTH, x, y, z, sl, cl, sp, cp)) return;
+    const double d2 = b200_nn_d2(x, y, z, tx, ty, tz);
+    if (d2 < best.d2 || (d2 == best.d2 && idx < best.idx)) {
+        best.d2 = d2;
+        best.idx = idx;
+    }
 }
 
 // EXACT search (float64 distances, float32 pre-filter).  Out of line: it only runs for the rare targets whose
@@ -143,10 +167,10 @@ __device__ __noinline__ long long nn_fixed_search_exact(const GeosDev &G, float 
             thr2 = fminf(thr2, t * t * 1.000001f);
         }
         // exact float64 evaluation of the few (usually one) that survive the pre-filter
-        if (d00 <= thr2) b200_nn_consider(G.pts + i00, tx, ty, tz, best);
-        if (d01 <= thr2) b200_nn_consider(G.pts + i00 + 1, tx, ty, tz, best);
-        if (d10 <= thr2) b200_nn_consider(G.pts + i00 + G.W, tx, ty, tz, best);
-        if (d11 <= thr2) b200_nn_consider(G.pts + i00 + G.W + 1, tx, ty, tz, best);
+        if (d00 <= thr2) nn_exact_consider(G, i00, tx, ty, tz, best);
+        if (d01 <= thr2) nn_exact_consider(G, i00 + 1, tx, ty, tz, best);
+        if (d10 <= thr2) nn_exact_consider(G, i00 + G.W, tx, ty, tz, best);
+        if (d11 <= thr2) nn_exact_consider(G, i00 + G.W + 1, tx, ty, tz, best);
     }
     // Any closer pixel lies inside the disc of radius w pixels around (fc, fr) (Euclidean bound above).
     const float bd = sqrtf((float)best.d2);
@@ -171,7 +195,7 @@ __device__ __noinline__ long long nn_fixed_search_exact(const GeosDev &G, float 
             const float d = nn_d2f(__ldg(G.pts32 + row_base + c), txf, tyf, tzf);
             if (d <= thr2) {
                 const double before = best.d2;
-                b200_nn_consider(G.pts + row_base + c, tx, ty, tz, best);
+                nn_exact_consider(G, row_base + c, tx, ty, tz, best);
                 if (best.d2 < before) {
                     const float t = sqrtf((float)best.d2) * 1.000001f + GEOS_F32_SLACK;
                     thr2 = fminf(thr2, t * t * 1.000001f);
@@ -189,6 +213,19 @@ __device__ __forceinline__ float nn_sqrt_approx(float x) {
     return r;
 }
 
+// MUFU.RSQ / MUFU.RCP without the denormal scaling of rsqrtf / __fdividef: the arguments are view-vector lengths of
+// 5 .. 7 earth radii (position only: 2^-22 relative is far below GEOS_POS_ERR)
+__device__ __forceinline__ float nn_rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float nn_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // two smallest float32 squared distances seen so far, branch-free.  Invalid pixels are stored as (+inf, 0, 0) in the
 // float32 copy, so their distance is +inf: it never becomes the minimum and leaves the runner-up at +inf.
 __device__ __forceinline__ void nn_track(float d, int idx, float &m1, int &i1, float &m2) {
@@ -203,10 +240,11 @@ __device__ __forceinline__ void nn_track(float d, int idx, float &m1, int &i1, f
 // if the leader is more than 1 m inside (outside) the radius it is accepted (rejected) exactly as float64 would.
 // Anything closer than that is re-done by nn_fixed_search_exact.
 #define GEOS_F32_ERR 1.0f
-// need_exact: the float32 ranking is ambiguous -- the caller runs nn_fixed_search_exact with the float64 coordinates.
-__device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc, float fr, float txf, float tyf,
-                                                     float tzf, bool &need_exact) {
-    need_exact = false;
+// Returns the raw source index, -1 (no neighbour within the radius) or GEOS_NEED_EXACT: the float32 ranking is
+// ambiguous -- the caller runs nn_fixed_search_exact with the float64 coordinates.  (n_src < 2^31: checked at build.)
+#define GEOS_NEED_EXACT (-2)
+__device__ __noinline__ int nn_fixed_search_general(const GeosDev &G, float fc, float fr, float txf, float tyf,
+                                                    float tzf) {
     const float reach = (float)G.max_ring + 1.0f;
     if (!(fc > -reach) || !(fc < (float)G.W + reach) || !(fr > -reach) || !(fr < (float)G.H + reach)) return -1;
     const int c0 = (int)floorf(fc), r0 = (int)floorf(fr);
@@ -341,11 +379,124 @@ __device__ __forceinline__ long long nn_fixed_search(const GeosDev &G, float fc,
     const bool clear_radius = fabsf(s1 - G.radius_f) > GEOS_F32_ERR + 0.01f;
     if (clear_winner && clear_radius) {
         if (!(s1 < G.radius_f)) GEOS_CNT(11);
-        return s1 < G.radius_f ? (long long)i1 : -1;
+        return s1 < G.radius_f ? i1 : -1;
     }
     GEOS_CNT(5);
-    need_exact = true;
-    return -1;
+    return GEOS_NEED_EXACT;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TIERED search: the hot path for radii of a few source pixels (every nearest-neighbour configuration of BASELINE.json).
+// Same float32 ranking and the same acceptance rules as nn_fixed_search_general, but the candidate sets are FIXED
+// stencils, so there is no loop, no lattice model and no per-row square root:
+//   tier 1   the 2 x 2 enclosing block.  Sufficient when every lattice point outside it is provably farther than the
+//            best distance found: they are at Euclidean grid distance >= 1 + (distance to the nearest block edge).
+//   tier 2   the other 12 points of the 4 x 4 window around the block; every lattice point outside the window is at
+//            grid distance >= 2 + (distance to the nearest block edge).
+//   else     nn_fixed_search_general (large radii, blocks at the border of the grid, strict mode).
+// The metres-per-pixel bound of the header (0.975 x pixel size) assumes both points at least h from the satellite.  At
+// the limb -- the only place where tier 1 does not suffice, because pixels are stretched radially there -- the points
+// are up to 1.163 h away, and the chord between two directions grows with the smaller of the two ranges:
+// d >= 2 rho_min sin(alpha / 2).  kf = min(1.10, 0.9999 + 0.36 (rho_T^2 / h^2 - 1)) <= rho / h for EVERY ellipsoid point
+// seen within 3 pixels of the target's direction (pixel angles up to 250 urad; scratch check: the smallest
+// rho_candidate / (h kf) over all view angles, azimuths, visible and just-hidden targets is 1.00009), so a grid distance
+// g is at least 0.975 kf g pixel_size metres.  With it the 4 x 4 window always covers the disc of a miss at radius
+// 2 x pixel size (w <= 2.07 / kf < 2), which a third of the far-limb targets are; without it a fifth of them fell
+// through to the general search.
+// Ranking keys: the float32 bits of the squared distance (monotone as unsigned integers) with the low four mantissa
+// bits replaced by the candidate's slot in the window -- min / max of integers track winner, slot and runner-up in
+// three instructions per candidate.  The four bits cost 2^-19 relative in d^2 (0.002 m at 2 km), inside the 0.01 m the
+// acceptance rules add for it.  Invalid pixels are (+inf, 0, 0): key >= 0x7f800000.
+#define GEOS_KEY_INF 0x7f800000u
+__device__ __forceinline__ void nn_key_track(const float4 &p, float tx, float ty, float tz, unsigned slot, unsigned &m1,
+                                             unsigned &m2) {
+    const unsigned k = (__float_as_uint(nn_d2f(p, tx, ty, tz)) & 0xfffffff0u) | slot;
+    m2 = min(m2, max(k, m1));
+    m1 = min(m1, k);
+}
+
+// Returns the raw index, -1, GEOS_NEED_EXACT or GEOS_DEFER (not settled here: run nn_fixed_search_general).  It never
+// calls an out-of-line routine itself, so that the caller's loop stays free of calls (their register conventions cost
+// the hot loop spills); callers collect the deferred targets and finish them afterwards (nn_fixed_search_finish).
+#define GEOS_DEFER (-3)
+__device__ __forceinline__ int nn_fixed_search(const GeosDev &G, float fc, float fr, float kf, float txf, float tyf,
+                                               float tzf) {
+    const int c0 = __float2int_rd(fc), r0 = __float2int_rd(fr);   // NaN -> 0, out of range saturates: not interior
+    if ((unsigned)(c0 - 1) >= (unsigned)G.Wm3 || (unsigned)(r0 - 1) >= (unsigned)G.Hm3) {
+        // far outside the grid (what nn_fixed_search_general rejects first): a miss; the border zone is deferred
+        const int reach = G.max_ring + 2;
+        if ((unsigned)(c0 + reach) >= (unsigned)(G.W + 2 * reach) || (unsigned)(r0 + reach) >= (unsigned)(G.H + 2 * reach))
+            return -1;
+        return GEOS_DEFER;
+    }
+    GEOS_CNT(0);
+    const int i00 = r0 * G.W + c0;
+    const float4 *q0 = G.pts32 + i00, *q1 = q0 + G.W;
+    unsigned m1, m2;
+    {
+        const float4 p00 = __ldg(q0), p01 = __ldg(q0 + 1), p10 = __ldg(q1), p11 = __ldg(q1 + 1);
+        const unsigned ka = (__float_as_uint(nn_d2f(p00, txf, tyf, tzf)) & 0xfffffff0u) | 5u;
+        const unsigned kb = (__float_as_uint(nn_d2f(p01, txf, tyf, tzf)) & 0xfffffff0u) | 6u;
+        m1 = min(ka, kb);
+        m2 = max(ka, kb);
+        nn_key_track(p10, txf, tyf, tzf, 9u, m1, m2);
+        nn_key_track(p11, txf, tyf, tzf, 10u, m1, m2);
+    }
+    // best distance so far: at most sqrt(m1) + 1 m (+ the key's four bits), never more than the radius (NaN: no valid
+    // pixel in the block -> fminf keeps the radius)
+    const float bd = fminf(G.radius_f, nn_sqrt_approx(__uint_as_float(m1)) + (GEOS_F32_ERR + 0.01f));
+    const float wq = bd * G.inv_step * 1.0001f;
+    const float fx = fc - (float)c0, fy = fr - (float)r0;
+    const float edge = fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy));
+    const float lim = (edge + (1.0f - GEOS_POS_ERR)) * kf;
+    if (!(wq < lim)) {
+        GEOS_CNT(1);
+        if (!(wq < lim + kf)) return GEOS_DEFER;
+        // three batches of four loads: twelve float4 in flight at once would take 48 registers
+        const float4 *qm = q0 - G.W, *q2 = q1 + G.W;
+        {
+            const float4 a0 = __ldg(qm - 1), a1 = __ldg(qm), a2 = __ldg(qm + 1), a3 = __ldg(qm + 2);
+            nn_key_track(a0, txf, tyf, tzf, 0u, m1, m2);
+            nn_key_track(a1, txf, tyf, tzf, 1u, m1, m2);
+            nn_key_track(a2, txf, tyf, tzf, 2u, m1, m2);
+            nn_key_track(a3, txf, tyf, tzf, 3u, m1, m2);
+        }
+        {
+            const float4 b0 = __ldg(q0 - 1), b3 = __ldg(q0 + 2), c0_ = __ldg(q1 - 1), c3 = __ldg(q1 + 2);
+            nn_key_track(b0, txf, tyf, tzf, 4u, m1, m2);
+            nn_key_track(b3, txf, tyf, tzf, 7u, m1, m2);
+            nn_key_track(c0_, txf, tyf, tzf, 8u, m1, m2);
+            nn_key_track(c3, txf, tyf, tzf, 11u, m1, m2);
+        }
+        {
+            const float4 d0 = __ldg(q2 - 1), d1 = __ldg(q2), d2 = __ldg(q2 + 1), d3 = __ldg(q2 + 2);
+            nn_key_track(d0, txf, tyf, tzf, 12u, m1, m2);
+            nn_key_track(d1, txf, tyf, tzf, 13u, m1, m2);
+            nn_key_track(d2, txf, tyf, tzf, 14u, m1, m2);
+            nn_key_track(d3, txf, tyf, tzf, 15u, m1, m2);
+        }
+    }
+    if (m1 >= GEOS_KEY_INF) {
+        GEOS_CNT(10);
+        return -1;  // no valid pixel within reach
+    }
+    const float s1 = nn_sqrt_approx(__uint_as_float(m1));
+    const float t = s1 + (2.0f * GEOS_F32_ERR + 0.02f);
+    const bool clear_winner = m2 > __float_as_uint(t * t * 1.000001f);
+    const bool clear_radius = fabsf(s1 - G.radius_f) > GEOS_F32_ERR + 0.02f;
+    if (clear_winner && clear_radius) {
+        const int slot = (int)(m1 & 15u);
+        return s1 < G.radius_f ? i00 + ((slot >> 2) - 1) * G.W + ((slot & 3) - 1) : -1;
+    }
+    GEOS_CNT(5);
+    return GEOS_NEED_EXACT;
+}
+
+// what nn_fixed_search left open for one target
+__device__ __forceinline__ long long nn_fixed_search_finish(const GeosDev &G, int found, float fc, float fr, double tx,
+                                                            double ty, double tz) {
+    if (found == GEOS_DEFER) found = nn_fixed_search_general(G, fc, fr, (float)tx, (float)ty, (float)tz);
+    return found == GEOS_NEED_EXACT ? nn_fixed_search_exact(G, fc, fr, tx, ty, tz) : (long long)found;
 }
 
 // atan for scan angles: a full disk stays below tan = 0.16, where the odd series to x^11 is exact to float32
@@ -363,18 +514,23 @@ __device__ __forceinline__ float nn_atan_scan(float x) {
 
 // target lon/lat -> fractional position in the source grid (PROJ geos forward, float32); false: far side.
 // Fast reciprocal / rsqrt are fine here: only the lattice position is needed (error << GEOS_POS_ERR pixels).
+// kf: the satellite-distance factor of the tiered search (see nn_fixed_search), from the squared range of the target
 __device__ __forceinline__ bool nn_fixed_position(const GeosDev &G, float rc, float rs, float s_rel, float c_rel,
-                                                  float &fc, float &fr) {
+                                                  float &fc, float &fr, float &kf) {
     float vx = rc * c_rel, vy = rc * s_rel, vz = rs;
     if (!(vx >= G.vis_min)) return false;
     float tmp = G.rg - vx;
     float ax, ay;
     if (G.sweep_x) {
-        ax = nn_atan_scan(vy * rsqrtf(fmaf(vz, vz, tmp * tmp)));
-        ay = nn_atan_scan(__fdividef(vz, tmp));
+        const float q = fmaf(vz, vz, tmp * tmp);
+        ax = nn_atan_scan(vy * nn_rsqrt_approx(q));
+        ay = nn_atan_scan(vz * nn_rcp_approx(tmp));
+        kf = fminf(G.k_cap, fmaf(fmaf(vy, vy, q), G.k_a, G.k_b));
     } else {
-        ax = nn_atan_scan(__fdividef(vy, tmp));
-        ay = nn_atan_scan(vz * rsqrtf(fmaf(vy, vy, tmp * tmp)));
+        const float q = fmaf(vy, vy, tmp * tmp);
+        ax = nn_atan_scan(vy * nn_rcp_approx(tmp));
+        ay = nn_atan_scan(vz * nn_rsqrt_approx(q));
+        kf = fminf(G.k_cap, fmaf(fmaf(vz, vz, q), G.k_a, G.k_b));
     }
     fc = fmaf(ax, G.col_scale, G.col_off);
     fr = fmaf(ay, G.row_scale, G.row_off);
@@ -404,11 +560,10 @@ __global__ void __launch_bounds__(256) nn_fixed_query_kernel(const __grid_consta
             float inv = rsqrtf(u * u + v * v);
             float cpg = u * inv, spg = v * inv;
             float rr = Q.G.rp * rsqrtf(Q.G.rp2 * cpg * cpg + spg * spg);
-            float fc, fr;
-            if (nn_fixed_position(Q.G, rr * cpg, rr * spg, s_rel, c_rel, fc, fr)) {
-                bool need_exact;
-                raw = nn_fixed_search(Q.G, fc, fr, (float)tx, (float)ty, (float)tz, need_exact);
-                if (need_exact) raw = nn_fixed_search_exact(Q.G, fc, fr, tx, ty, tz);
+            float fc, fr, kf;
+            if (nn_fixed_position(Q.G, rr * cpg, rr * spg, s_rel, c_rel, fc, fr, kf)) {
+                const int found = nn_fixed_search(Q.G, fc, fr, kf, (float)tx, (float)ty, (float)tz);
+                raw = found >= -1 ? (long long)found : nn_fixed_search_finish(Q.G, found, fc, fr, tx, ty, tz);
             }
         }
         b200_nn_emit(Q.O, Q.G.prefix, i, raw, ok);
@@ -425,6 +580,22 @@ nn_seg_cmax_kernel(const TgtCol *__restrict__ cols, int W, int nseg, float *__re
     for (int c = warp * 256 + lane; c < min(W, warp * 256 + 256); c += 32) m = fmaxf(m, cols[c].c_rel);
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) seg_cmax[warp] = m;
+}
+
+// One target of a rectilinear grid that the tiered search left open: everything recomputed from the tables (rare).
+template <bool FUSED1>
+__device__ __noinline__ void nn_rect_finish_item(const GeosQueryArg &Q, int r, int col, int found) {
+    const TgtRow R = Q.rows[r];
+    const TgtCol Cc = Q.cols[col];
+    long long raw = -1;
+    float fc, fr, kf;
+    if (nn_fixed_position(Q.G, R.rc, R.rs, Cc.s_rel, Cc.c_rel, fc, fr, kf))
+        raw = nn_fixed_search_finish(Q.G, found, fc, fr, R.dlam * Cc.cos_lam, R.dlam * Cc.sin_lam, R.dlam1);
+    const int64_t i = (int64_t)r * Q.dst.width + col;
+    if (FUSED1)
+        st_stream_f1(Q.O.out + i, raw < 0 ? Q.O.fill : __ldg(Q.O.data + raw));
+    else
+        b200_nn_emit(Q.O, Q.G.prefix, i, raw, true);
 }
 
 // rectilinear targets: one work item = 256 consecutive columns of one row, tables instead of trigonometry; items are
@@ -494,6 +665,15 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
             if (tail + (int64_t)threadIdx.x < n) st_stream_f1(dst + tail + threadIdx.x, Q.O.fill);
             continue;
         }
+        // FUSED1: the gather of item k is issued at the end of its iteration and stored at the end of the NEXT one, so
+        // the load's latency (a DRAM access for most pixels) is covered by the next item's search instead of stalling
+        // the warp in front of the store.  Targets the tiered search does not settle (0.3 %: float32 ranking ambiguous,
+        // block at the border of the grid) only set a bit; they are finished after the loop, which therefore contains
+        // no call.
+        const int r_first = r, seg_first = seg;
+        unsigned todo = 0u;
+        float pend_v = 0.0f;
+        float *pend_p = nullptr;
         for (int k = 0; k < count; ++k, ++seg) {
             if (seg == nseg) {
                 seg = 0;
@@ -521,28 +701,71 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
                 continue;
             }
             if (col >= W) continue;
-            const TgtRow R = Q.rows[r];
-            const TgtCol Cc = Q.cols[col];
-            const bool ok = Cc.valid;
-            long long raw = -1;
-            float fc, fr;
-            if (ok && nn_fixed_position(Q.G, R.rc, R.rs, Cc.s_rel, Cc.c_rel, fc, fr)) {
+            const TgtRow *Rp = Q.rows + r;
+            const TgtCol *Cp = Q.cols + col;
+            // FUSED1 never reports validity: an invalid column carries c_rel = NaN (nn_target_tables_kernel), fails the
+            // visibility test of nn_fixed_position and becomes a miss without its flag being read
+            const bool ok = FUSED1 ? true : (Cp->valid != 0);
+            int found = -1;
+            float fc, fr, kf;
+            // one 128-bit load each: {dlam, rc, rs} of the row, {sin_lam, cos_lam} of the column (nn_common.cuh)
+            const double2 rw = __ldg(reinterpret_cast<const double2 *>(&Rp->dlam));
+            const float rc = __int_as_float(__double2loint(rw.y)), rs = __int_as_float(__double2hiint(rw.y));
+            const float2 rel = __ldg(reinterpret_cast<const float2 *>(&Cp->s_rel));
+            if (ok && nn_fixed_position(Q.G, rc, rs, rel.x, rel.y, fc, fr, kf)) {
                 // R.dlam = R_earth cos(phi), R.dlam1 = R_earth sin(phi), R.b_lo = float32 bits of the latter (nn.cu)
-                const double tx = R.dlam * Cc.cos_lam, ty = R.dlam * Cc.sin_lam;
-                bool need_exact;
-                raw = nn_fixed_search(Q.G, fc, fr, (float)tx, (float)ty, __int_as_float(R.b_lo), need_exact);
-                if (need_exact) raw = nn_fixed_search_exact(Q.G, fc, fr, tx, ty, R.dlam1);
+                const double2 sc = __ldg(reinterpret_cast<const double2 *>(&Cp->sin_lam));
+                const double tx = rw.x * sc.y, ty = rw.x * sc.x;
+                found = nn_fixed_search(Q.G, fc, fr, kf, (float)tx, (float)ty, __int_as_float(Rp->b_lo));
             }
-            if (FUSED1)
-                st_stream_f1(Q.O.out + i, raw < 0 ? Q.O.fill : __ldg(Q.O.data + raw));
-            else
-                b200_nn_emit(Q.O, Q.G.prefix, i, raw, ok);
+            if (found < -1) {
+                todo |= (found == GEOS_DEFER ? 0x10000u : 1u) << k;
+                continue;
+            }
+            if (FUSED1) {
+                if (pend_p) st_stream_f1(pend_p, pend_v);
+                pend_p = Q.O.out + i;
+                pend_v = found < 0 ? Q.O.fill : __ldg(Q.O.data + found);
+            } else {
+                b200_nn_emit(Q.O, Q.G.prefix, i, (long long)found, ok);
+            }
+        }
+        if (FUSED1 && pend_p) st_stream_f1(pend_p, pend_v);
+        while (todo) {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            int sk = seg_first + (bit & 15), rk = r_first;
+            while (sk >= nseg) {
+                sk -= nseg;
+                ++rk;
+            }
+            nn_rect_finish_item<FUSED1>(Q, rk, sk * 256 + (int)threadIdx.x, bit >= 16 ? GEOS_DEFER : GEOS_NEED_EXACT);
         }
     }
 }
 
+static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst, double radius, const QueryOut &O,
+                                    cudaStream_t s, const GeosFast &fast);
+
 int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, double radius, const QueryOut &O,
                              cudaStream_t s) {
+    GeosFast fast;
+    memset(&fast, 0, sizeof(fast));
+    if (g->light) {
+        if (O.index_array) {
+            b200_set_error("b200_nn_query: a light search structure (fused path) has no compressed index table");
+            return B200_EUNSUPPORTED;
+        }
+        int rc = b200_geos_fast_prepare(&g->src, &fast, s);   // the exact path recomputes float64 points from these
+        if (rc) return rc;
+    }
+    const int rc = nn_fixed_grid_query_impl(g, dst, radius, O, s, fast);
+    if (g->light) b200_geos_fast_release(&fast, s);
+    return rc;
+}
+
+static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst, double radius, const QueryOut &O,
+                                    cudaStream_t s, const GeosFast &fast) {
     const b200_geo_t &src = g->src;
     const b200_proj_t &P = src.area.proj;
     GeosQueryArg Q;
@@ -551,6 +774,8 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
     Q.cols = nullptr;
     Q.rows = nullptr;
     GeosDev &G = Q.G;
+    G.fast = fast;
+    G.src_row0 = src.row0;
     G.pts = g->pts;
     G.pts32 = g->pts32;
     G.prune = g->strict ? 0 : 1;
@@ -585,6 +810,20 @@ int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, doubl
         return B200_EUNSUPPORTED;
     }
     G.max_ring = (int32_t)rings;
+    // tiered search (nn_fixed_search): fixed stencils reach radii up to ~2.5 source pixels; strict mode never uses them.
+    // The satellite-distance factor was verified for geostationary heights and pixel angles up to 250 urad
+    // (kf = 1 otherwise: the plain bound).
+    G.Wm3 = g->strict ? 0 : (int32_t)(src.width > 3 ? src.width - 3 : 0);
+    G.Hm3 = g->strict ? 0 : (int32_t)(src.nrows > 3 ? src.nrows - 3 : 0);
+    {
+        const double ang = fmax(src.area.pixel_size_x, src.area.pixel_size_y) / hm;
+        const bool kf_ok = P.p[0] > 5.3 && P.p[0] < 5.9 && ang <= 250e-6;
+        const double c1 = kf_ok ? 0.36 : 0.0;
+        // rho^2 / h^2 in units of the kernel's view vector (semi-major axes): (a / h)^2 = 1 / p0^2
+        G.k_a = (float)(c1 / (P.p[0] * P.p[0]));
+        G.k_b = (float)(kf_ok ? 0.9999 - c1 : 1.0);
+        G.k_cap = (float)(kf_ok ? 1.10 : 1.0);
+    }
     // visible iff vx >= 1 / radius_g (PROJ geos forward); keep hidden points up to 1.5 radii behind the limb
     G.vis_min = (float)(1.0 / P.p[1] - 1.5 * radius / P.a - 1e-5);
 
@@ -773,7 +1012,8 @@ __global__ void __launch_bounds__(128) bil_info_kernel(const __grid_constant__ B
             float inv = rsqrtf(u * u + v * v);
             float cpg = u * inv, spg = v * inv;
             float rr = G.rp * rsqrtf(G.rp2 * cpg * cpg + spg * spg);
-            have_pos = nn_fixed_position(G, rr * cpg, rr * spg, s_rel, c_rel, fc, fr);
+            float kf_;
+            have_pos = nn_fixed_position(G, rr * cpg, rr * spg, s_rel, c_rel, fc, fr, kf_);
         }
         const float reach = Q.w_max + 1.0f;
         if (have_pos && fc > -reach && fc < (float)G.W + reach && fr > -reach && fr < (float)G.H + reach) {
@@ -917,7 +1157,13 @@ extern "C" int b200_bil_info(const b200_nn_grid_t *grid, const uint8_t *valid_in
     const b200_proj_t &P = src.area.proj;
     BilArg Q;
     Q.dst = *dst;
+    if (grid->light) {
+        b200_set_error("b200_bil_info: needs a full search structure (float64 records), not a light one");
+        return B200_EUNSUPPORTED;
+    }
     GeosDev &G = Q.G;
+    memset(&G.fast, 0, sizeof(G.fast));
+    G.src_row0 = src.row0;
     G.pts = grid->pts;
     G.pts32 = grid->pts32;
     G.prune = 0;
@@ -944,6 +1190,9 @@ extern "C" int b200_bil_info(const b200_nn_grid_t *grid, const uint8_t *valid_in
     double rings = ceil(radius / step + GEOS_POS_ERR) + 1.0;
     if (rings > 4096.0) rings = 4096.0;
     G.max_ring = (int32_t)rings;
+    G.Wm3 = G.Hm3 = 0;   // (the tiered nearest search is not used here)
+    G.k_a = 0.0f;
+    G.k_b = G.k_cap = 1.0f;
     G.vis_min = (float)(1.0 / P.p[1] - 1.5 * radius / P.a - 1e-5);
     Q.w_max = (float)rings;
     Q.neighbours = neighbours;

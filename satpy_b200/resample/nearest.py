@@ -47,6 +47,7 @@ from ..geometry import AreaDefinition, SwathDefinition, as_geometry
 LOG = logging.getLogger(__name__)
 
 SEARCH_METHODS = {"auto": 0, "bucket": 1, "fixed_grid": 2, "fixed_grid_strict": 3}
+NN_LIGHT = 0x100   # B200_NN_LIGHT (include/satpy_b200.h)
 
 NN_COORDINATES = {"valid_input_index": ("y1", "x1"),
                   "valid_output_index": ("y2", "x2"),
@@ -149,8 +150,10 @@ class B200NearestResampler(_compat.resampler_base()):
         m = m.to("cuda").to(torch.uint8).contiguous()
         return m, m.data_ptr()
 
-    def _build_grid(self, torch, radius, method, mask_ptr=None, want_count=True):
-        """``(grid, valid_input, n_valid or None)``: the search structure over the valid source points."""
+    def _build_grid(self, torch, radius, method, mask_ptr=None, want_count=True, light=False):
+        """``(grid, valid_input, n_valid or None)``: the search structure over the valid source points.
+        ``light``: float32 points only (``B200_NN_LIGHT``) -- for the fused search+gather, which never asks for
+        compressed indices or the count."""
         lib = _lib.load()
         src = self.source_geo_def
         valid_input = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
@@ -159,7 +162,8 @@ class B200NearestResampler(_compat.resampler_base()):
         gs = src.geo_struct()
         _lib.check(lib.b200_nn_grid_create_ex(C.byref(gs), mask_ptr, radius, valid_input.data_ptr(),
                                               C.byref(n_valid) if want_count else None, C.byref(handle),
-                                              SEARCH_METHODS[method], _lib.stream_ptr(torch)))
+                                              SEARCH_METHODS[method] | (NN_LIGHT if light and not want_count else 0),
+                                              _lib.stream_ptr(torch)))
         return _Grid(handle), valid_input, (int(n_valid.value) if want_count else None)
 
     def precompute(self, mask=None, radius_of_influence=None, epsilon=0, cache_dir=None, row_window=None,
@@ -529,7 +533,7 @@ class B200NearestResampler(_compat.resampler_base()):
         if tr is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
-        grid, _valid_input, _ = self._build_grid(torch, radius, method, None, want_count=False)
+        grid, _valid_input, _ = self._build_grid(torch, radius, method, None, want_count=False, light=True)
         if tr is not None:
             ev[1].record()
         host_arr = None

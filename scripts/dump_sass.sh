@@ -12,7 +12,7 @@ declare -A K=(
   [sunz_fast_fused_abi]=_Z16sunz_fast_kernelILi1ELb1EEv11SunzFastArg7SunzDev
   [abi_calibrate_lane]=_Z25abi_calibrate_lane_kernelILb0EEvPKsPfl9AbiCalDev
   [abi_calibrate_bulk]=_Z25abi_calibrate_bulk_kernelILb0EEvPKsPfl9AbiCalDev
-  [nn_gather_bulk]=_Z21nn_gather_bulk_kernelPKjPjPKilj
+  [nn_gather_bulk]=_Z21nn_gather_bulk_kernelILb0EEvPKjPjPKiljill
   [nn_gather_direct]=_Z16nn_gather_kernelIjEvPKT_PS0_PKilillS0_
 )
 CENSUS=profiles/${ROUND}_sass_census.txt

@@ -95,3 +95,66 @@ def test_c2_one_search_serves_three_bands_full_size():
     o8 = r.compute(u8, fill_value=255)
     gi = r._current["gather_index"]
     assert o8.dtype == torch.uint8 and bool((o8[gi < 0] == 255).all())
+
+
+def test_c5_tiered_search_equals_strict_mode_on_the_whole_target(c5):
+    """The fixed 2x2 / 4x4 stencils with the satellite-distance factor (``fixed_grid``) against the general loop that
+    examines every lattice point of the rigorous disc (``fixed_grid_strict``) on EVERY pixel of config 5, band by band."""
+    import torch
+    src, dst, _ = c5
+    hits = 0
+    step = 4008
+    for row0 in range(0, dst.height, step):
+        n = min(step, dst.height - row0)
+        out = {}
+        for method in ("fixed_grid", "fixed_grid_strict"):
+            r = B200NearestResampler(src, dst)
+            r.precompute(radius_of_influence=2000.0, row_window=(row0, n), method=method, gather_only=True)
+            out[method] = r._current["gather_index"]
+            del r
+        diff = int((out["fixed_grid"] != out["fixed_grid_strict"]).sum())
+        assert diff == 0, f"rows {row0}..{row0 + n}: {diff} pixels differ"
+        hits += int((out["fixed_grid"] >= 0).sum())
+        del out
+    assert 0.25 < hits / dst.size < 0.45
+
+
+def test_light_search_structure_serves_the_fused_path_only():
+    """``B200_NN_LIGHT``: float32 points only.  The fused search+gather and raw gather indices work (and equal the
+    full structure's, exact float64 decisions included); what needs the prefix table or the float64 records is
+    refused with B200_EUNSUPPORTED."""
+    import ctypes as C
+    import torch
+    from satpy_b200 import _lib
+    from satpy_b200.resample.nearest import NN_LIGHT, SEARCH_METHODS
+    lib = _lib.load()
+    stream = _lib.stream_ptr(torch)
+    src, dst = demo.make_area("goes_east_abi_f_2km"), demo.make_area("goes_east_eqc_2km")
+    data = torch.rand(src.shape, device="cuda", dtype=torch.float32)
+    gs, gd = src.geo_struct(), dst.geo_struct()
+    res = {}
+    for light in (0, NN_LIGHT):
+        vin = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
+        h = C.c_void_p(None)
+        _lib.check(lib.b200_nn_grid_create_ex(C.byref(gs), None, 5000.0, vin.data_ptr(), None, C.byref(h),
+                                              SEARCH_METHODS["fixed_grid"] | light, stream))
+        out = torch.empty(dst.shape, dtype=torch.float32, device="cuda")
+        gi = torch.empty(dst.shape, dtype=torch.int32, device="cuda")
+        _lib.check(lib.b200_nn_query_gather_f32(h, C.byref(gd), 5000.0, data.data_ptr(), out.data_ptr(), 1, 0, 0,
+                                                float("nan"), stream))
+        _lib.check(lib.b200_nn_query(h, C.byref(gd), 5000.0, None, gi.data_ptr(), None, stream))
+        nbytes = C.c_int64(0)
+        _lib.check(lib.b200_nn_grid_nbytes(h, C.byref(nbytes)))
+        if light:
+            ia = torch.empty(dst.shape, dtype=torch.int32, device="cuda")
+            assert lib.b200_nn_query(h, C.byref(gd), 5000.0, ia.data_ptr(), None, None, stream) == _lib.B200_EUNSUPPORTED
+            nv = C.c_int64(0)
+            assert lib.b200_nn_grid_n_valid(h, C.byref(nv)) == _lib.B200_EUNSUPPORTED
+        torch.cuda.synchronize()
+        res[light] = (out, gi, vin, nbytes.value)
+        lib.b200_nn_grid_destroy(h)
+    (o0, g0, v0, b0), (o1, g1, v1, b1) = res[0], res[NN_LIGHT]
+    assert b1 == src.size * 16 and b0 == src.size * 52
+    assert bool((g0 == g1).all()) and bool((v0 == v1).all())
+    assert bool(((o0 == o1) | (torch.isnan(o0) & torch.isnan(o1))).all())
+    assert 0.3 < float((g0 >= 0).float().mean()) < 0.9
