@@ -570,16 +570,17 @@ __global__ void __launch_bounds__(256) nn_fixed_query_kernel(const __grid_consta
     }
 }
 
-// per 256-column segment of a rectilinear target: the largest cos(lon - lon_0) of its columns.  A segment whose every
-// column is on the far side for a given row (rc * cmax < vis_min) is filled without any per-pixel work.
+// per group of GEOS_TILE_COLS columns of a rectilinear target: the largest cos(lon - lon_0) of its columns.  A group whose
+// every column is on the far side for a given row (rc * cmax < vis_min) is filled without any per-pixel work.
+#define GEOS_TILE_COLS 32   /* one warp */
+#define GEOS_TILE_ROWS 16
 __global__ void __launch_bounds__(256)
-nn_seg_cmax_kernel(const TgtCol *__restrict__ cols, int W, int nseg, float *__restrict__ seg_cmax) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nseg) return;
+nn_seg_cmax_kernel(const TgtCol *__restrict__ cols, int W, int ngroups, float *__restrict__ seg_cmax) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
     float m = -2.0f;
-    for (int c = warp * 256 + lane; c < min(W, warp * 256 + 256); c += 32) m = fmaxf(m, cols[c].c_rel);
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) seg_cmax[warp] = m;
+    for (int c = g * GEOS_TILE_COLS; c < min(W, (g + 1) * GEOS_TILE_COLS); ++c) m = fmaxf(m, cols[c].c_rel);   // NaN ignored
+    seg_cmax[g] = m;
 }
 
 // One target of a rectilinear grid that the tiered search left open: everything recomputed from the tables (rare).
@@ -598,149 +599,120 @@ __device__ __noinline__ void nn_rect_finish_item(const GeosQueryArg &Q, int r, i
         b200_nn_emit(Q.O, Q.G.prefix, i, raw, true);
 }
 
-// rectilinear targets: one work item = 256 consecutive columns of one row, tables instead of trigonometry; items are
-// handed out in order through an atomic counter (chunks of GEOS_CHUNK consecutive segments).
+// Rectilinear targets (lon from the column, lat from the row): tables instead of trigonometry, and one WARP per work
+// unit -- a tile of GEOS_TILE_ROWS consecutive rows x 32 consecutive columns, walked row by row:
+//   * a lane keeps its column for the whole tile: the column's table entry is read once and stays in registers;
+//   * consecutive rows of a tile fall into the same or the next source rows, so the source points a row loads are the
+//     ones the previous row left in L1 (the row-major order of the first release re-read them from L2 for every row:
+//     L1 hit rate 47 %, 67 GB of L2 -> L1 traffic per launch);
+//   * no block-level barrier: a warp draws its next tile from the atomic queue by itself, one tile ahead, so the
+//     latency of the atomic is covered by the tile in hand (the per-CTA queue cost 13 % of the stall cycles at its two
+//     barriers per chunk);
+//   * tiles are handed out in row-band-major order, so all warps of the device sweep one compact front of 16 target
+//     rows and the source rows they share stay in L2 although the cost per tile varies 10x (on / off the disk).
+// A warp retires after GEOS_TILES_PER_WARP tiles, so SM slots keep freeing up for work on other streams (the exchange of
+// the previous row block) while this kernel runs.
 // FUSED1: the hot configuration -- fused gather of one float32 band, no index outputs.
-#define GEOS_CHUNK 16
-#define GEOS_CHUNKS_PER_CTA 8
+#define GEOS_TILES_PER_WARP 16
+#define GEOS_TILES_PER_DRAW 2   /* power of two, divides GEOS_TILES_PER_WARP */
+#define GEOS_WARPS_PER_CTA 4
 template <bool FUSED1>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(GEOS_WARPS_PER_CTA * 32, 8)
 nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long long *__restrict__ queue,
-                           const float *__restrict__ seg_cmax) {
-    const int W = (int)Q.dst.width;
-    const int nseg = (W + 255) >> 8;
-    const long long items = (long long)Q.dst.nrows * nseg;
-    const int lane = threadIdx.x & 31;
-    __shared__ int s_row, s_seg, s_count;
-    // Each CTA takes GEOS_CHUNKS_PER_CTA chunks from the queue and retires: CTAs keep sweeping one compact front of
-    // target rows (the queue hands chunks out in order), but SM slots free up all the time, so that a collective
-    // issued on another stream (the all-gather of the previous row block) gets SMs while this kernel runs.
-    for (int turn = 0; turn < GEOS_CHUNKS_PER_CTA; ++turn) {
-        if (threadIdx.x == 0) {
-            long long first = (long long)atomicAdd(queue, (unsigned long long)GEOS_CHUNK);
-            long long left = items - first;
-            s_count = left <= 0 ? 0 : (left < GEOS_CHUNK ? (int)left : GEOS_CHUNK);
-            if (left > 0) {
-                long long r = first / nseg;
-                s_row = (int)r;
-                s_seg = (int)(first - r * nseg);
-            }
+                           const float *__restrict__ seg_cmax, unsigned ngroups, unsigned ntiles) {
+    const int W = (int)Q.dst.width, H = (int)Q.dst.nrows;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned draw = 0u;   // first tile of the pair in hand (a draw = GEOS_TILES_PER_DRAW consecutive tiles, one atomic)
+    if (lane == 0u) draw = (unsigned)atomicAdd(queue, (unsigned long long)GEOS_TILES_PER_DRAW);
+    draw = __shfl_sync(0xffffffffu, draw, 0);
+    unsigned nxt = 0xffffffffu;
+#pragma unroll 1
+    for (int turn = 0; turn < GEOS_TILES_PER_WARP && draw < ntiles; ++turn) {
+        const unsigned cur = draw + ((unsigned)turn & (GEOS_TILES_PER_DRAW - 1));
+        if ((turn & (GEOS_TILES_PER_DRAW - 1)) == 0) {
+            nxt = 0xffffffffu;   // the draw after this one: requested now, used GEOS_TILES_PER_DRAW tiles later
+            if (lane == 0u && turn + GEOS_TILES_PER_DRAW < GEOS_TILES_PER_WARP)
+                nxt = (unsigned)atomicAdd(queue, (unsigned long long)GEOS_TILES_PER_DRAW);
         }
-        __syncthreads();
-        const int count = s_count;
-        int r = s_row, seg = s_seg;
-        __syncthreads();
-        if (count == 0) break;
-        // Which items of the chunk can see the satellite at all?  Lane k looks at item k, so the (row, segment) table
-        // reads of the whole chunk are in flight together instead of one dependent read per item.
+        if (cur >= ntiles) break;
+        const unsigned band = cur / ngroups, grp = cur - band * ngroups;
+        const int r_first = (int)band * GEOS_TILE_ROWS;
+        const int count = min(GEOS_TILE_ROWS, H - r_first);
+        const int col = (int)grp * GEOS_TILE_COLS + (int)lane;
+        // Which rows of the tile can see the satellite at all?  Lane k looks at row k: the table reads of the whole tile
+        // are in flight together.
         bool vis = false;
-        if (lane < count) {
-            int rk = r, sk = seg + lane;
-            while (sk >= nseg) {
-                sk -= nseg;
-                ++rk;
-            }
-            const TgtRow *Rk = Q.rows + rk;
-            vis = Rk->valid && (Rk->rc * __ldg(seg_cmax + sk) >= Q.G.vis_min);
+        if ((int)lane < count) {
+            const TgtRow *Rk = Q.rows + r_first + lane;
+            vis = Rk->valid && (Rk->rc * __ldg(seg_cmax + grp) >= Q.G.vis_min);
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, vis);
-        int64_t row_base = (int64_t)r * W;
-        if (FUSED1 && vmask == 0u) {
-            // The whole chunk is on the far side.  Its items cover one contiguous range of the output (segments
-            // tile the rows in memory order): all threads fill it with 128-bit stores.
-            int sl = seg + count - 1, rl = r;
-            while (sl >= nseg) {
-                sl -= nseg;
-                ++rl;
-            }
-            float *dst = Q.O.out + row_base + (int64_t)seg * 256;
-            const int64_t n = ((int64_t)rl * W + min(sl * 256 + 256, W)) - (row_base + (int64_t)seg * 256);
-            const int64_t head = min(n, (int64_t)(((16 - (((uintptr_t)dst) & 15)) & 15) >> 2));
-            if ((int64_t)threadIdx.x < head) st_stream_f1(dst + threadIdx.x, Q.O.fill);
-            const int64_t nvec = (n - head) >> 2;
-            float *body = dst + head;
-            for (int64_t j = threadIdx.x; j < nvec; j += 256)
-                st_stream_f4(body + 4 * j, Q.O.fill, Q.O.fill, Q.O.fill, Q.O.fill);
-            const int64_t tail = head + 4 * nvec;
-            if (tail + (int64_t)threadIdx.x < n) st_stream_f1(dst + tail + threadIdx.x, Q.O.fill);
-            continue;
-        }
-        // FUSED1: the gather of item k is issued at the end of its iteration and stored at the end of the NEXT one, so
-        // the load's latency (a DRAM access for most pixels) is covered by the next item's search instead of stalling
-        // the warp in front of the store.  Targets the tiered search does not settle (0.3 %: float32 ranking ambiguous,
-        // block at the border of the grid) only set a bit; they are finished after the loop, which therefore contains
-        // no call.
-        const int r_first = r, seg_first = seg;
-        unsigned todo = 0u;
-        float pend_v = 0.0f;
-        float *pend_p = nullptr;
-        for (int k = 0; k < count; ++k, ++seg) {
-            if (seg == nseg) {
-                seg = 0;
-                ++r;
-                row_base += W;
-            }
-            const int col = seg * 256 + (int)threadIdx.x;
-            const int64_t i = row_base + col;
-            if (!((vmask >> k) & 1u)) {
-                // nothing of this segment can see the satellite: every pixel is a miss
+        const bool in_w = col < W;
+        const int64_t i_first = (int64_t)r_first * W + col;
+        if (vmask == 0u) {
+            // the whole tile is on the far side: every pixel is a miss
+            if (in_w) {
                 if (FUSED1) {
-                    if (threadIdx.x < 64) {  // two warps write the 1 KB of the segment, the others move on
-                        const int n = min(256, W - seg * 256);
-                        float *dst = Q.O.out + row_base + seg * 256;
-                        // rows are 8-byte aligned at worst (even widths): peel to a 16-byte boundary
-                        const int head = (int)(((16 - (((uintptr_t)dst) & 15)) & 15) >> 2);
-                        const int j = head + (int)threadIdx.x * 4;
-                        if (j + 3 < n) st_stream_f4(dst + j, Q.O.fill, Q.O.fill, Q.O.fill, Q.O.fill);
-                        else for (int k2 = j; k2 < n; ++k2) st_stream_f1(dst + k2, Q.O.fill);
-                        if ((int)threadIdx.x < head && (int)threadIdx.x < n) st_stream_f1(dst + threadIdx.x, Q.O.fill);
-                    }
-                } else if (col < W) {
-                    b200_nn_emit(Q.O, Q.G.prefix, i, -1, Q.rows[r].valid && Q.cols[col].valid);
+                    float *dst = Q.O.out + i_first;
+                    for (int k = 0; k < count; ++k, dst += W) st_stream_f1(dst, Q.O.fill);
+                } else {
+                    const bool cv = Q.cols[col].valid != 0;
+                    for (int k = 0; k < count; ++k)
+                        b200_nn_emit(Q.O, Q.G.prefix, i_first + (int64_t)k * W, -1, cv && Q.rows[r_first + k].valid);
                 }
-                continue;
             }
-            if (col >= W) continue;
-            const TgtRow *Rp = Q.rows + r;
+        } else if (in_w) {
+            // the lane's column: {sin_lam, cos_lam} and {s_rel, c_rel}, one 128-bit and one 64-bit load per TILE
             const TgtCol *Cp = Q.cols + col;
+            const double2 sc = __ldg(reinterpret_cast<const double2 *>(&Cp->sin_lam));
+            const float2 rel = __ldg(reinterpret_cast<const float2 *>(&Cp->s_rel));
             // FUSED1 never reports validity: an invalid column carries c_rel = NaN (nn_target_tables_kernel), fails the
             // visibility test of nn_fixed_position and becomes a miss without its flag being read
             const bool ok = FUSED1 ? true : (Cp->valid != 0);
-            int found = -1;
-            float fc, fr, kf;
-            // one 128-bit load each: {dlam, rc, rs} of the row, {sin_lam, cos_lam} of the column (nn_common.cuh)
-            const double2 rw = __ldg(reinterpret_cast<const double2 *>(&Rp->dlam));
-            const float rc = __int_as_float(__double2loint(rw.y)), rs = __int_as_float(__double2hiint(rw.y));
-            const float2 rel = __ldg(reinterpret_cast<const float2 *>(&Cp->s_rel));
-            if (ok && nn_fixed_position(Q.G, rc, rs, rel.x, rel.y, fc, fr, kf)) {
-                // R.dlam = R_earth cos(phi), R.dlam1 = R_earth sin(phi), R.b_lo = float32 bits of the latter (nn.cu)
-                const double2 sc = __ldg(reinterpret_cast<const double2 *>(&Cp->sin_lam));
-                const double tx = rw.x * sc.y, ty = rw.x * sc.x;
-                found = nn_fixed_search(Q.G, fc, fr, kf, (float)tx, (float)ty, __int_as_float(Rp->b_lo));
+            // FUSED1: the gather of row k is issued at the end of its iteration and stored at the end of the NEXT one,
+            // so the load's latency (a DRAM access for most pixels) is covered by the next row's search instead of
+            // stalling the warp in front of the store.  Targets the tiered search does not settle (0.3 %: float32
+            // ranking ambiguous, block at the border of the grid) only set a bit; they are finished after the loop,
+            // which therefore contains no call.
+            unsigned todo = 0u;
+            float pend_v = 0.0f;
+            int pend_k = -1;
+            float *const out0 = FUSED1 ? Q.O.out + i_first : nullptr;
+            for (int k = 0; k < count; ++k) {
+                int found = -1;
+                if ((vmask >> k) & 1u) {
+                    // {dlam, rc, rs} of the row: one 128-bit load, the same address for every lane
+                    const TgtRow *Rp = Q.rows + r_first + k;
+                    const double2 rw = __ldg(reinterpret_cast<const double2 *>(&Rp->dlam));
+                    const float rc = __int_as_float(__double2loint(rw.y)), rs = __int_as_float(__double2hiint(rw.y));
+                    float fc, fr, kf;
+                    if (ok && nn_fixed_position(Q.G, rc, rs, rel.x, rel.y, fc, fr, kf)) {
+                        // R.dlam = R_earth cos(phi), R.dlam1 = R_earth sin(phi), R.b_lo = float32 bits of the latter
+                        const double tx = rw.x * sc.y, ty = rw.x * sc.x;
+                        found = nn_fixed_search(Q.G, fc, fr, kf, (float)tx, (float)ty, __int_as_float(__ldg(&Rp->b_lo)));
+                    }
+                    if (found < -1) {
+                        todo |= (found == GEOS_DEFER ? 0x10000u : 1u) << k;
+                        continue;
+                    }
+                }
+                if (FUSED1) {
+                    if (pend_k >= 0) st_stream_f1(out0 + pend_k * W, pend_v);
+                    pend_k = k;
+                    pend_v = found < 0 ? Q.O.fill : __ldg(Q.O.data + found);
+                } else {
+                    b200_nn_emit(Q.O, Q.G.prefix, i_first + (int64_t)k * W, (long long)found,
+                                 ok && ((vmask >> k) & 1u ? true : Q.rows[r_first + k].valid != 0));
+                }
             }
-            if (found < -1) {
-                todo |= (found == GEOS_DEFER ? 0x10000u : 1u) << k;
-                continue;
-            }
-            if (FUSED1) {
-                if (pend_p) st_stream_f1(pend_p, pend_v);
-                pend_p = Q.O.out + i;
-                pend_v = found < 0 ? Q.O.fill : __ldg(Q.O.data + found);
-            } else {
-                b200_nn_emit(Q.O, Q.G.prefix, i, (long long)found, ok);
+            if (FUSED1 && pend_k >= 0) st_stream_f1(out0 + pend_k * W, pend_v);
+            while (todo) {
+                const int bit = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                nn_rect_finish_item<FUSED1>(Q, r_first + (bit & 15), col, bit >= 16 ? GEOS_DEFER : GEOS_NEED_EXACT);
             }
         }
-        if (FUSED1 && pend_p) st_stream_f1(pend_p, pend_v);
-        while (todo) {
-            const int bit = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            int sk = seg_first + (bit & 15), rk = r_first;
-            while (sk >= nseg) {
-                sk -= nseg;
-                ++rk;
-            }
-            nn_rect_finish_item<FUSED1>(Q, rk, sk * 256 + (int)threadIdx.x, bit >= 16 ? GEOS_DEFER : GEOS_NEED_EXACT);
-        }
+        if ((turn & (GEOS_TILES_PER_DRAW - 1)) == GEOS_TILES_PER_DRAW - 1) draw = __shfl_sync(0xffffffffu, nxt, 0);
     }
 }
 
@@ -836,22 +808,31 @@ static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst
         Q.rows = rows;
         unsigned long long *queue = nullptr;
         float *seg_cmax = nullptr;
-        const int nseg = (int)((dst->width + 255) / 256);
+        const int64_t ngroups = (dst->width + GEOS_TILE_COLS - 1) / GEOS_TILE_COLS;
+        const int64_t ntiles = ngroups * ((dst->nrows + GEOS_TILE_ROWS - 1) / GEOS_TILE_ROWS);
+        if (ntiles >= (1LL << 31) || (int64_t)GEOS_TILE_ROWS * dst->width >= (1LL << 31)) {
+            cudaFreeAsync(cols, s);
+            cudaFreeAsync(rows, s);
+            b200_set_error("b200_nn_query: target too large for one call (%lld tiles): query it in row bands",
+                           (long long)ntiles);
+            return B200_EUNSUPPORTED;
+        }
         cudaError_t e = cudaMallocAsync((void **)&queue, sizeof(unsigned long long), s);
-        if (e == cudaSuccess) e = cudaMallocAsync((void **)&seg_cmax, (size_t)nseg * sizeof(float), s);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&seg_cmax, (size_t)ngroups * sizeof(float), s);
         if (e == cudaSuccess) e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s);
         if (e == cudaSuccess) {
-            nn_seg_cmax_kernel<<<(nseg * 32 + 255) / 256, 256, 0, s>>>(cols, (int)dst->width, nseg, seg_cmax);
-            int64_t items = dst->nrows * (int64_t)nseg;
-            const int64_t chunks = (items + GEOS_CHUNK - 1) / GEOS_CHUNK;
-            int grid = (int)((chunks + GEOS_CHUNKS_PER_CTA - 1) / GEOS_CHUNKS_PER_CTA);
+            nn_seg_cmax_kernel<<<(int)((ngroups + 255) / 256), 256, 0, s>>>(cols, (int)dst->width, (int)ngroups, seg_cmax);
+            const int64_t per_cta = (int64_t)GEOS_TILES_PER_WARP * GEOS_WARPS_PER_CTA;
+            int grid = (int)((ntiles + per_cta - 1) / per_cta);
             if (grid < 1) grid = 1;
             const bool fused1 = O.out != nullptr && O.nbands == 1 && !O.index_array && !O.gather_index &&
                                 !O.valid_output;
             if (fused1)
-                nn_fixed_query_rect_kernel<true><<<grid, 256, 0, s>>>(Q, queue, seg_cmax);
+                nn_fixed_query_rect_kernel<true><<<grid, GEOS_WARPS_PER_CTA * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
+                                                                                    (unsigned)ntiles);
             else
-                nn_fixed_query_rect_kernel<false><<<grid, 256, 0, s>>>(Q, queue, seg_cmax);
+                nn_fixed_query_rect_kernel<false><<<grid, GEOS_WARPS_PER_CTA * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
+                                                                                     (unsigned)ntiles);
             e = cudaGetLastError();
         }
         if (queue) cudaFreeAsync(queue, s);
