@@ -104,7 +104,10 @@ nn_source_points_kernel(const __grid_constant__ SrcArg S, const uint8_t *__restr
             p[0] = make_double2(x, y);
             p[1] = make_double2(z, __longlong_as_double((long long)i));
         }
-        if (rec32) rec32[i] = ok ? make_float4((float)x, (float)y, (float)z, 0.0f)
+        // float32 copy; w carries what the rounding dropped, per coordinate, as signed 10-bit multiples of 2^-11 m
+        // (|residual| <= 0.25 m for |coordinate| < 2^23 m): nn_geos.cu re-ranks near-ties with these 0.5 mm points
+        // instead of going back to the float64 records (nn_fixed_refine)
+        if (rec32) rec32[i] = ok ? make_float4((float)x, (float)y, (float)z, __int_as_float(b200_pack_residuals(x, y, z)))
                                  : make_float4(__int_as_float(0x7f800000), 0.0f, 0.0f, 0.0f);
         if (cell_of) cell_of[i] = ok ? b200_cell_of(band_off, lam, phi, phi0, inv_dphi, nbands) : -1;
     }

@@ -80,6 +80,23 @@ __device__ __forceinline__ void b200_lonlat2xyz(double lon, double lat, double &
     z = B200_R_EARTH * sp;
 }
 
+// Rounding residuals of a float32 point, packed into one word: per coordinate rint((v - (float)v) * 2048) clamped to
+// +-511 (10 bits, two's complement), x in bits 0-9, y in 10-19, z in 20-29.  v ~ (float)v + r * 2^-11 to 2^-11 m.
+#define B200_RES_SCALE 2048.0
+__device__ __forceinline__ int b200_pack_residuals(double x, double y, double z) {
+    const int rx = max(-511, min(511, __double2int_rn((x - (double)(float)x) * B200_RES_SCALE)));
+    const int ry = max(-511, min(511, __double2int_rn((y - (double)(float)y) * B200_RES_SCALE)));
+    const int rz = max(-511, min(511, __double2int_rn((z - (double)(float)z) * B200_RES_SCALE)));
+    return (rx & 0x3ff) | ((ry & 0x3ff) << 10) | ((rz & 0x3ff) << 20);
+}
+// the refined point: float32 value + residual, in float64
+__device__ __forceinline__ void b200_refined_point(const float4 &p, double &x, double &y, double &z) {
+    const int w = __float_as_int(p.w);
+    x = (double)p.x + (double)((w << 22) >> 22) * (1.0 / B200_RES_SCALE);
+    y = (double)p.y + (double)((w << 12) >> 22) * (1.0 / B200_RES_SCALE);
+    z = (double)p.z + (double)((w << 2) >> 22) * (1.0 / B200_RES_SCALE);
+}
+
 struct Best {
     double d2;
     long long idx;

@@ -492,10 +492,59 @@ __device__ __forceinline__ int nn_fixed_search(const GeosDev &G, float fc, float
     return GEOS_NEED_EXACT;
 }
 
+// REFINED ranking of a target whose float32 ranking was ambiguous (0.3 % of config 5: two pixels within 2 m of each
+// other, or the nearest within 1 m of the radius).  The float32 points carry their rounding residuals (w, multiples of
+// 2^-11 m; nn_source_points_kernel), so every candidate of the 4 x 4 window is known to 2^-11 m per coordinate:
+// distances good to GEOS_REFINED_ERR = 1 mm, against 1 m for the float32 ranking.  The window is a superset of what the
+// tiered search proved sufficient, so its exact nearest is the nearest.  Only what is still ambiguous at the millimetre
+// -- systematic ties of symmetric geometries, one target in 10^5 -- goes on to nn_fixed_search_exact; before, every
+// ambiguous target walked its disc again and recomputed or re-read float64 points (13 % of the kernel's instructions
+// at 1.5 active lanes).  Only called for interior blocks (GEOS_NEED_EXACT from nn_fixed_search).
+#define GEOS_REFINED_ERR 1.0e-3
+__device__ __noinline__ int nn_fixed_refine(const GeosDev &G, float fc, float fr, double tx, double ty, double tz) {
+    const int c0 = __float2int_rd(fc), r0 = __float2int_rd(fr);
+    const float txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
+    const float4 *q = G.pts32 + ((r0 - 1) * G.W + c0 - 1);
+    // float32 pass over the window: the smallest distance, then only what lies within 3 m of it is refined
+    float m = __int_as_float(0x7f800000);
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) m = fminf(m, nn_d2f(__ldg(q + j * G.W + i), txf, tyf, tzf));
+    if (!(m < __int_as_float(0x7f800000))) return -1;
+    const float lim = sqrtf(m) + (2.0f * GEOS_F32_ERR + 1.0f);
+    const float lim2 = lim * lim * 1.000001f;
+    double b1 = __longlong_as_double(0x7ff0000000000000LL), b2 = b1;   // two smallest refined squared distances
+    int i1 = -1;
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
+            const float4 p = __ldg(q + j * G.W + i);
+            if (!(nn_d2f(p, txf, tyf, tzf) <= lim2)) continue;
+            double x, y, z;
+            b200_refined_point(p, x, y, z);
+            const double d2 = b200_nn_d2(x, y, z, tx, ty, tz);
+            if (d2 < b1) {
+                b2 = b1;
+                b1 = d2;
+                i1 = (r0 - 1 + j) * G.W + c0 - 1 + i;
+            } else if (d2 < b2) {
+                b2 = d2;
+            }
+        }
+    const double s1 = sqrt(b1), t = s1 + 2.5 * GEOS_REFINED_ERR;
+    const double radius = sqrt(G.r2);
+    if (!(b2 > t * t) || fabs(s1 - radius) < 1.25 * GEOS_REFINED_ERR) return GEOS_NEED_EXACT;
+    return s1 < radius ? i1 : -1;
+}
+
 // what nn_fixed_search left open for one target
 __device__ __forceinline__ long long nn_fixed_search_finish(const GeosDev &G, int found, float fc, float fr, double tx,
                                                             double ty, double tz) {
-    if (found == GEOS_DEFER) found = nn_fixed_search_general(G, fc, fr, (float)tx, (float)ty, (float)tz);
+    if (found == GEOS_DEFER) {
+        found = nn_fixed_search_general(G, fc, fr, (float)tx, (float)ty, (float)tz);
+    } else if (found == GEOS_NEED_EXACT) {
+        GEOS_CNT(12);
+        found = nn_fixed_refine(G, fc, fr, tx, ty, tz);
+    }
+    if (found == GEOS_NEED_EXACT) GEOS_CNT(13);
     return found == GEOS_NEED_EXACT ? nn_fixed_search_exact(G, fc, fr, tx, ty, tz) : (long long)found;
 }
 
@@ -613,13 +662,13 @@ __device__ __noinline__ void nn_rect_finish_item(const GeosQueryArg &Q, int r, i
 // A warp retires after GEOS_TILES_PER_WARP tiles, so SM slots keep freeing up for work on other streams (the exchange of
 // the previous row block) while this kernel runs.
 // FUSED1: the hot configuration -- fused gather of one float32 band, no index outputs.
-#define GEOS_TILES_PER_WARP 16
-#define GEOS_TILES_PER_DRAW 2   /* power of two, divides GEOS_TILES_PER_WARP */
-#define GEOS_WARPS_PER_CTA 4
+#define GEOS_TILES_PER_WARP 64
+#define GEOS_TILES_PER_DRAW 2   /* power of two, divides the tiles per warp */
+#define GEOS_WARPS_PER_CTA 1   /* measured: 1 x 64 tiles 13.11 ms, 2 x 64 13.18, 4 x 64 13.32, 4 x 16 13.75 (scripts/query_knobs.sh) */
 template <bool FUSED1>
-__global__ void __launch_bounds__(GEOS_WARPS_PER_CTA * 32, 8)
+__global__ void __launch_bounds__(128, 8)   // 64 registers; launched with GEOS_WARPS_PER_CTA warps (up to 4 via the knob)
 nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long long *__restrict__ queue,
-                           const float *__restrict__ seg_cmax, unsigned ngroups, unsigned ntiles) {
+                           const float *__restrict__ seg_cmax, unsigned ngroups, unsigned ntiles, int tiles_per_warp) {
     const int W = (int)Q.dst.width, H = (int)Q.dst.nrows;
     const unsigned lane = threadIdx.x & 31u;
     unsigned draw = 0u;   // first tile of the pair in hand (a draw = GEOS_TILES_PER_DRAW consecutive tiles, one atomic)
@@ -627,11 +676,11 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
     draw = __shfl_sync(0xffffffffu, draw, 0);
     unsigned nxt = 0xffffffffu;
 #pragma unroll 1
-    for (int turn = 0; turn < GEOS_TILES_PER_WARP && draw < ntiles; ++turn) {
+    for (int turn = 0; turn < tiles_per_warp && draw < ntiles; ++turn) {
         const unsigned cur = draw + ((unsigned)turn & (GEOS_TILES_PER_DRAW - 1));
         if ((turn & (GEOS_TILES_PER_DRAW - 1)) == 0) {
             nxt = 0xffffffffu;   // the draw after this one: requested now, used GEOS_TILES_PER_DRAW tiles later
-            if (lane == 0u && turn + GEOS_TILES_PER_DRAW < GEOS_TILES_PER_WARP)
+            if (lane == 0u && turn + GEOS_TILES_PER_DRAW < tiles_per_warp)
                 nxt = (unsigned)atomicAdd(queue, (unsigned long long)GEOS_TILES_PER_DRAW);
         }
         if (cur >= ntiles) break;
@@ -822,17 +871,27 @@ static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst
         if (e == cudaSuccess) e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s);
         if (e == cudaSuccess) {
             nn_seg_cmax_kernel<<<(int)((ngroups + 255) / 256), 256, 0, s>>>(cols, (int)dst->width, (int)ngroups, seg_cmax);
-            const int64_t per_cta = (int64_t)GEOS_TILES_PER_WARP * GEOS_WARPS_PER_CTA;
+            // tuning knobs for measurements (scripts/query_knobs.sh); the defaults are what the library ships with
+            static int warps_per_cta = 0, tiles_per_warp = 0;
+            if (warps_per_cta == 0) {
+                const char *e1 = getenv("B200_NN_WARPS_PER_CTA"), *e2 = getenv("B200_NN_TILES_PER_WARP");
+                int w = e1 ? atoi(e1) : GEOS_WARPS_PER_CTA, t = e2 ? atoi(e2) : GEOS_TILES_PER_WARP;
+                if (w != 1 && w != 2 && w != 4) w = GEOS_WARPS_PER_CTA;
+                if (t < GEOS_TILES_PER_DRAW || t > 4096 || (t % GEOS_TILES_PER_DRAW)) t = GEOS_TILES_PER_WARP;
+                tiles_per_warp = t;
+                warps_per_cta = w;
+            }
+            const int64_t per_cta = (int64_t)tiles_per_warp * warps_per_cta;
             int grid = (int)((ntiles + per_cta - 1) / per_cta);
             if (grid < 1) grid = 1;
             const bool fused1 = O.out != nullptr && O.nbands == 1 && !O.index_array && !O.gather_index &&
                                 !O.valid_output;
             if (fused1)
-                nn_fixed_query_rect_kernel<true><<<grid, GEOS_WARPS_PER_CTA * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
-                                                                                    (unsigned)ntiles);
+                nn_fixed_query_rect_kernel<true><<<grid, warps_per_cta * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
+                                                                               (unsigned)ntiles, tiles_per_warp);
             else
-                nn_fixed_query_rect_kernel<false><<<grid, GEOS_WARPS_PER_CTA * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
-                                                                                     (unsigned)ntiles);
+                nn_fixed_query_rect_kernel<false><<<grid, warps_per_cta * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
+                                                                                (unsigned)ntiles, tiles_per_warp);
             e = cudaGetLastError();
         }
         if (queue) cudaFreeAsync(queue, s);
