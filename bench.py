@@ -520,7 +520,8 @@ def run_b200(args):
                "pcie_gbs": (h2d + d2h) / ms_e2e / 1e6,
                "note": "per rank: calibrate_abi(numpy counts) -> SunZenithCorrector -> B200NearestResampler.resample("
                        "to_host=True) -> numpy image of this rank's rows in page-locked memory; the rows are produced in "
-                       "24 bands, each copied out while the next is searched; of every band only the column span the disk "
+                       "row bands (~256 MB each), each copied out while the next is searched; of every "
+                       f"{B200NearestResampler.SPAN_ROWS} rows only the column span the disk "
                        "can reach crosses PCIe (d2h_bytes_per_step), host threads write the fill value into the rest of "
                        "the image (host_image_bytes_per_step is the whole image); bytes are per rank"}
         if world == 1 and args.scale == 1.0:

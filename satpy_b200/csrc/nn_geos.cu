@@ -85,6 +85,7 @@ struct GeosDev {
     float r2_slack;                 // (radius + GEOS_F32_SLACK)^2 * (1 + eps)
     float k_a, k_b, k_cap;          // satellite-distance factor of the tiered search: min(k_cap, k_a * rho^2 + k_b)
     int32_t Wm3, Hm3;               // max(0, W - 3), max(0, H - 3): blocks whose 4 x 4 window lies inside the grid
+    uint32_t key_mask, pad2_;       // 0xfffffff0, as a kernel argument (see nn_key)
     double r2;
 };
 
@@ -408,9 +409,18 @@ __device__ __noinline__ int nn_fixed_search_general(const GeosDev &G, float fc, 
 // three instructions per candidate.  The four bits cost 2^-19 relative in d^2 (0.002 m at 2 km), inside the 0.01 m the
 // acceptance rules add for it.  Invalid pixels are (+inf, 0, 0): key >= 0x7f800000.
 #define GEOS_KEY_INF 0x7f800000u
-__device__ __forceinline__ void nn_key_track(const float4 &p, float tx, float ty, float tz, unsigned slot, unsigned &m1,
+// key = (distance bits & 0xfffffff0) | slot in ONE LOP3: the mask comes in as a kernel argument, because with two
+// literal constants ptxas emits an AND and an OR (one immediate operand per instruction)
+template <unsigned SLOT>
+__device__ __forceinline__ unsigned nn_key(const GeosDev &G, const float4 &p, float tx, float ty, float tz) {
+    unsigned k;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEC;" : "=r"(k) : "r"(__float_as_uint(nn_d2f(p, tx, ty, tz))), "n"(SLOT), "r"(G.key_mask));
+    return k;
+}
+template <unsigned SLOT>
+__device__ __forceinline__ void nn_key_track(const GeosDev &G, const float4 &p, float tx, float ty, float tz, unsigned &m1,
                                              unsigned &m2) {
-    const unsigned k = (__float_as_uint(nn_d2f(p, tx, ty, tz)) & 0xfffffff0u) | slot;
+    const unsigned k = nn_key<SLOT>(G, p, tx, ty, tz);
     m2 = min(m2, max(k, m1));
     m1 = min(m1, k);
 }
@@ -435,12 +445,11 @@ __device__ __forceinline__ int nn_fixed_search(const GeosDev &G, float fc, float
     unsigned m1, m2;
     {
         const float4 p00 = __ldg(q0), p01 = __ldg(q0 + 1), p10 = __ldg(q1), p11 = __ldg(q1 + 1);
-        const unsigned ka = (__float_as_uint(nn_d2f(p00, txf, tyf, tzf)) & 0xfffffff0u) | 5u;
-        const unsigned kb = (__float_as_uint(nn_d2f(p01, txf, tyf, tzf)) & 0xfffffff0u) | 6u;
+        const unsigned ka = nn_key<5u>(G, p00, txf, tyf, tzf), kb = nn_key<6u>(G, p01, txf, tyf, tzf);
         m1 = min(ka, kb);
         m2 = max(ka, kb);
-        nn_key_track(p10, txf, tyf, tzf, 9u, m1, m2);
-        nn_key_track(p11, txf, tyf, tzf, 10u, m1, m2);
+        nn_key_track<9u>(G, p10, txf, tyf, tzf, m1, m2);
+        nn_key_track<10u>(G, p11, txf, tyf, tzf, m1, m2);
     }
     // best distance so far: at most sqrt(m1) + 1 m (+ the key's four bits), never more than the radius (NaN: no valid
     // pixel in the block -> fminf keeps the radius)
@@ -452,28 +461,30 @@ __device__ __forceinline__ int nn_fixed_search(const GeosDev &G, float fc, float
     if (!(wq < lim)) {
         GEOS_CNT(1);
         if (!(wq < lim + kf)) return GEOS_DEFER;
-        // three batches of four loads: twelve float4 in flight at once would take 48 registers
+        // Three batches of four loads (twelve float4 in flight at once would take 48 registers).  The row above the block
+        // is at grid distance >= fy + 1 and the row below at >= 2 - fy: each is examined only if that is within reach --
+        // the lanes of a warp are neighbours on one target row and mostly agree, so one of the two is usually skipped.
         const float4 *qm = q0 - G.W, *q2 = q1 + G.W;
-        {
+        if (!(wq < (fy + (1.0f - GEOS_POS_ERR)) * kf)) {
             const float4 a0 = __ldg(qm - 1), a1 = __ldg(qm), a2 = __ldg(qm + 1), a3 = __ldg(qm + 2);
-            nn_key_track(a0, txf, tyf, tzf, 0u, m1, m2);
-            nn_key_track(a1, txf, tyf, tzf, 1u, m1, m2);
-            nn_key_track(a2, txf, tyf, tzf, 2u, m1, m2);
-            nn_key_track(a3, txf, tyf, tzf, 3u, m1, m2);
+            nn_key_track<0u>(G, a0, txf, tyf, tzf, m1, m2);
+            nn_key_track<1u>(G, a1, txf, tyf, tzf, m1, m2);
+            nn_key_track<2u>(G, a2, txf, tyf, tzf, m1, m2);
+            nn_key_track<3u>(G, a3, txf, tyf, tzf, m1, m2);
         }
         {
             const float4 b0 = __ldg(q0 - 1), b3 = __ldg(q0 + 2), c0_ = __ldg(q1 - 1), c3 = __ldg(q1 + 2);
-            nn_key_track(b0, txf, tyf, tzf, 4u, m1, m2);
-            nn_key_track(b3, txf, tyf, tzf, 7u, m1, m2);
-            nn_key_track(c0_, txf, tyf, tzf, 8u, m1, m2);
-            nn_key_track(c3, txf, tyf, tzf, 11u, m1, m2);
+            nn_key_track<4u>(G, b0, txf, tyf, tzf, m1, m2);
+            nn_key_track<7u>(G, b3, txf, tyf, tzf, m1, m2);
+            nn_key_track<8u>(G, c0_, txf, tyf, tzf, m1, m2);
+            nn_key_track<11u>(G, c3, txf, tyf, tzf, m1, m2);
         }
-        {
+        if (!(wq < ((2.0f - GEOS_POS_ERR) - fy) * kf)) {
             const float4 d0 = __ldg(q2 - 1), d1 = __ldg(q2), d2 = __ldg(q2 + 1), d3 = __ldg(q2 + 2);
-            nn_key_track(d0, txf, tyf, tzf, 12u, m1, m2);
-            nn_key_track(d1, txf, tyf, tzf, 13u, m1, m2);
-            nn_key_track(d2, txf, tyf, tzf, 14u, m1, m2);
-            nn_key_track(d3, txf, tyf, tzf, 15u, m1, m2);
+            nn_key_track<12u>(G, d0, txf, tyf, tzf, m1, m2);
+            nn_key_track<13u>(G, d1, txf, tyf, tzf, m1, m2);
+            nn_key_track<14u>(G, d2, txf, tyf, tzf, m1, m2);
+            nn_key_track<15u>(G, d3, txf, tyf, tzf, m1, m2);
         }
     }
     if (m1 >= GEOS_KEY_INF) {
@@ -665,8 +676,10 @@ __device__ __noinline__ void nn_rect_finish_item(const GeosQueryArg &Q, int r, i
 #define GEOS_TILES_PER_WARP 64
 #define GEOS_TILES_PER_DRAW 2   /* power of two, divides the tiles per warp */
 #define GEOS_WARPS_PER_CTA 1   /* measured: 1 x 64 tiles 13.11 ms, 2 x 64 13.18, 4 x 64 13.32, 4 x 16 13.75 (scripts/query_knobs.sh) */
+// 64 registers (32 warps / SM).  A 48-register build (40 warps / SM, 68 instead of 44 bytes of spills) measured the same:
+// 12.95 against 12.99 ms with two warps per CTA.
 template <bool FUSED1>
-__global__ void __launch_bounds__(128, 8)   // 64 registers; launched with GEOS_WARPS_PER_CTA warps (up to 4 via the knob)
+__global__ void __launch_bounds__(128, 8)   // launched with GEOS_WARPS_PER_CTA warps (up to 4 via the knob)
 nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long long *__restrict__ queue,
                            const float *__restrict__ seg_cmax, unsigned ngroups, unsigned ntiles, int tiles_per_warp) {
     const int W = (int)Q.dst.width, H = (int)Q.dst.nrows;
@@ -834,6 +847,8 @@ static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst
     // tiered search (nn_fixed_search): fixed stencils reach radii up to ~2.5 source pixels; strict mode never uses them.
     // The satellite-distance factor was verified for geostationary heights and pixel angles up to 250 urad
     // (kf = 1 otherwise: the plain bound).
+    G.key_mask = 0xfffffff0u;
+    G.pad2_ = 0;
     G.Wm3 = g->strict ? 0 : (int32_t)(src.width > 3 ? src.width - 3 : 0);
     G.Hm3 = g->strict ? 0 : (int32_t)(src.nrows > 3 ? src.nrows - 3 : 0);
     {
@@ -886,12 +901,13 @@ static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst
             if (grid < 1) grid = 1;
             const bool fused1 = O.out != nullptr && O.nbands == 1 && !O.index_array && !O.gather_index &&
                                 !O.valid_output;
+            const dim3 block(warps_per_cta * 32);
             if (fused1)
-                nn_fixed_query_rect_kernel<true><<<grid, warps_per_cta * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
-                                                                               (unsigned)ntiles, tiles_per_warp);
+                nn_fixed_query_rect_kernel<true><<<grid, block, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups, (unsigned)ntiles,
+                                                                      tiles_per_warp);
             else
-                nn_fixed_query_rect_kernel<false><<<grid, warps_per_cta * 32, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups,
-                                                                                (unsigned)ntiles, tiles_per_warp);
+                nn_fixed_query_rect_kernel<false><<<grid, block, 0, s>>>(Q, queue, seg_cmax, (unsigned)ngroups, (unsigned)ntiles,
+                                                                       tiles_per_warp);
             e = cudaGetLastError();
         }
         if (queue) cudaFreeAsync(queue, s);
@@ -1230,6 +1246,8 @@ extern "C" int b200_bil_info(const b200_nn_grid_t *grid, const uint8_t *valid_in
     double rings = ceil(radius / step + GEOS_POS_ERR) + 1.0;
     if (rings > 4096.0) rings = 4096.0;
     G.max_ring = (int32_t)rings;
+    G.key_mask = 0xfffffff0u;
+    G.pad2_ = 0;
     G.Wm3 = G.Hm3 = 0;   // (the tiered nearest search is not used here)
     G.k_a = 0.0f;
     G.k_b = G.k_cap = 1.0f;

@@ -107,6 +107,7 @@ class B200NearestResampler(_compat.resampler_base()):
     """Nearest-neighbour resampling on one B200."""
 
     ROW_CHUNKS = 24  # host results: rows are produced in this many bands, each copied out while the next is computed
+    SPAN_ROWS = 208  # host results: rows per reachable-column span (one device->host copy each; 8 per band of config 5)
     trace = None     # set to a list to collect (stage, start event, end event) of the fused path (bench.py)
 
     def __init__(self, source_geo_def, target_geo_def):
@@ -358,48 +359,63 @@ class B200NearestResampler(_compat.resampler_base()):
         width = out.shape[-1]
         bands = []
         for r0, n in self._row_bands(nrows, True):
-            span = (0, width)
-            if radius is not None and out.dtype == torch.float32:
-                span = parallel.block_column_span(self.source_geo_def, self.target_geo_def, row0 + r0, n, radius)
-            bands.append((r0, n, span))
+            # the span is taken per SUB-band of ~SPAN_ROWS rows: a band of config 5 is 7.5 degrees of latitude, over
+            # which the disk's outline moves by up to 25 degrees of longitude; one span per band shipped 5.8 GB for
+            # 4.7 GB of disk
+            subs = []
+            for s0 in range(0, n, self.SPAN_ROWS):
+                sn = min(self.SPAN_ROWS, n - s0)
+                span = (0, width)
+                if radius is not None and out.dtype == torch.float32:
+                    span = parallel.block_column_span(self.source_geo_def, self.target_geo_def, row0 + r0 + s0, sn, radius)
+                subs.append((r0 + s0, sn, span))
+            bands.append((r0, n, subs))
         h3 = host_t.reshape(-1, nrows, width)
         total = nrows * width
-        if not _xfer.spans_pay_off(total, sum(n * max(0, sp[1] - sp[0]) for _, n, sp in bands)):
-            bands = [(r0, n, (0, width)) for r0, n, _ in bands]
-        fut = _xfer.fill_async(h3, [(r0, n, sp) for r0, n, sp in bands if sp != (0, width)], fill_value)
+        spanned = sum(sn * max(0, sp[1] - sp[0]) for _, _, subs in bands for _, sn, sp in subs)
+        if not _xfer.spans_pay_off(total, spanned):
+            bands = [(r0, n, [(r0, n, (0, width))]) for r0, n, _ in bands]
+            spanned = total
+        fut = _xfer.fill_async(h3, [sub for _, _, subs in bands for sub in subs if sub[2] != (0, width)], fill_value)
         # bytes that actually cross PCIe for this result (bench.py reports them)
-        self.last_d2h_bytes = int(sum(n * max(0, sp[1] - sp[0]) for _, n, sp in bands) * h3.shape[0] * out.element_size())
+        self.last_d2h_bytes = int(spanned * h3.shape[0] * out.element_size())
         return host_t, host_arr, h3, bands, fut
 
     @staticmethod
-    def _band_to_host(torch, cs, h3, out3, r0, n, span):
-        """Queue the device->host copy of one finished row band (its reachable columns) on the copy stream."""
+    def _band_to_host(torch, cs, h3, out3, r0, n, subs):
+        """Queue the device->host copies of one finished row band on the copy stream: per sub-band of rows, the columns
+        the source can reach (``subs`` from ``_host_plan``: ``[(row0, nrows, (c_lo, c_hi)), ...]``)."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         cs.wait_event(ev)
-        c_lo, c_hi = span
-        if c_hi <= c_lo:
-            return
         width = out3.shape[-1]
+        esize = out3.element_size()
+        lib = None
         with torch.cuda.stream(cs):
-            if (c_lo, c_hi) == (0, width):
-                h3[:, r0:r0 + n].copy_(out3[:, r0:r0 + n], non_blocking=True)
-            else:
-                esize = out3.element_size()
-                lib = _lib.load()
+            for s0, sn, (c_lo, c_hi) in subs:
+                if c_hi <= c_lo:
+                    continue
+                if (c_lo, c_hi) == (0, width):
+                    h3[:, s0:s0 + sn].copy_(out3[:, s0:s0 + sn], non_blocking=True)
+                    continue
+                lib = lib or _lib.load()
                 for b in range(out3.shape[0]):
-                    _lib.check(lib.b200_copy_2d(h3[b, r0, c_lo:].data_ptr(), width * esize, out3[b, r0, c_lo:].data_ptr(),
-                                                width * esize, (c_hi - c_lo) * esize, n, int(cs.cuda_stream)))
+                    _lib.check(lib.b200_copy_2d(h3[b, s0, c_lo:].data_ptr(), width * esize, out3[b, s0, c_lo:].data_ptr(),
+                                                width * esize, (c_hi - c_lo) * esize, sn, int(cs.cuda_stream)))
 
     def _row_bands(self, nrows, to_host):
         width = self.target_geo_def.width
-        # bands start on 16-byte boundaries of the index / output rows; a band is worth ~256 MB of result (each costs
-        # three launches and a span computation on the host): 24 for the 12.85 GB of config 5, 2 for an eighth of it
+        # a band is worth ~256 MB of result (each costs three launches and a span computation on the host): 24 for the
+        # 12.85 GB of config 5, 2 for an eighth of it.  Bands start on multiples of four rows, i.e. on 16-byte
+        # boundaries of the index / output arrays whatever the width (the first release only cut widths divisible by
+        # four into bands: config 5's 80150 columns went out as ONE band, copied after the last kernel, under the
+        # bounding box of the whole disk)
         n = 1
-        if to_host and width % 4 == 0:
+        if to_host:
             n = max(1, min(self.ROW_CHUNKS, (nrows * width * 4) >> 28))
         rows = -(-nrows // max(1, n))
-        return [(r0, min(rows, nrows - r0)) for r0 in range(0, nrows, max(1, rows))]
+        rows = max(4, -(-rows // 4) * 4)
+        return [(r0, min(rows, nrows - r0)) for r0 in range(0, nrows, rows)]
 
     def compute(self, data, weight_funcs=None, fill_value=np.nan, with_uncert=False, to_host=None, out=None, **kwargs):
         """``get_sample_from_neighbour_info``: gather ``data`` through the cached indices.
@@ -436,7 +452,7 @@ class B200NearestResampler(_compat.resampler_base()):
         fill_buf = (C.c_char * elem).from_buffer_copy(fill.tobytes())
         lib = _lib.load()
         host_arr = None
-        bands = [(r0, n, (0, width)) for r0, n in self._row_bands(nrows, False)]
+        bands = [(r0, n, None) for r0, n in self._row_bands(nrows, False)]
         if to_host:
             cur = self._cur
             host_t, host_arr, h3, bands, fut = self._host_plan(torch, out, cur["row_window"][0], nrows,
@@ -537,7 +553,7 @@ class B200NearestResampler(_compat.resampler_base()):
         if tr is not None:
             ev[1].record()
         host_arr = None
-        bands = [(r0, n, (0, width)) for r0, n in self._row_bands(nrows, False)]
+        bands = [(r0, n, None) for r0, n in self._row_bands(nrows, False)]
         _t1 = _time.perf_counter()
         if to_host:
             host_t, host_arr, h3, bands, fut = self._host_plan(torch, out, row0, nrows, radius, float(fill_value))

@@ -1,7 +1,12 @@
 #!/bin/bash
-# A/B of the query kernel's launch shape (warps per CTA x tiles per warp) on config 5, one B200:
+# A/B of the query kernel's launch shape on config 5, one B200 (warps per CTA, tiles per warp, 48-register variant):
 #   gpurun -- bash scripts/query_knobs.sh > gpurun_out/query_knobs.txt
-for w in 4 2 1; do for t in 16 64; do
-  B200_NN_WARPS_PER_CTA=$w B200_NN_TILES_PER_WARP=$t python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-stages 2>/dev/null |
-    python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('warps/CTA $w tiles/warp $t: step', round(d['ms_per_step'],3), 'ms, query', round(d['stages']['query_gather']['ms'],3), 'ms')"
-done; done
+run() {
+  B200_NN_WARPS_PER_CTA=$1 B200_NN_TILES_PER_WARP=$2 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-stages 2>/dev/null |
+    python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('warps/CTA $1 tiles/warp $2: step', round(d['ms_per_step'],3), 'ms, query', round(d['stages']['query_gather']['ms'],3), 'ms')"
+}
+run 1 64 0
+run 2 64 0
+
+
+run 1 128 0
