@@ -65,6 +65,8 @@ def _fill_threads():
             cores = os.cpu_count() or 1
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
         _FILL_THREADS = max(1, min(16, cores // local_world))
+        if os.environ.get("B200_FILL_THREADS"):        # measurements (scripts/e2e_probe.py)
+            _FILL_THREADS = max(1, int(os.environ["B200_FILL_THREADS"]))
     return _FILL_THREADS
 
 
@@ -100,39 +102,58 @@ def spans_pay_off(total_bytes, span_bytes):
 
 def fill_async(host3, bands, value):
     """Write ``value`` into the columns outside ``[c_lo, c_hi)`` of the given row bands of a page-locked result
-    ``host3`` (bands, rows, width) on worker threads (PyTorch's CPU fill releases the GIL), while the caller queues
-    device work.  ``bands``: ``[(row0, nrows, (c_lo, c_hi)), ...]``.  Returns an object with ``.result()``."""
+    ``host3`` (bands, rows, width) on worker threads (the library's host helper and PyTorch's CPU fill release the
+    GIL), while the caller queues device work.  ``bands``: ``[(row0, nrows, (c_lo, c_hi)), ...]``.  Returns an object
+    with ``.result()``.
+
+    The rectangles are cut into about four tasks per thread of similar size (rows of large rectangles are split, small
+    rectangles are batched): a result with 200 row bands used to submit 6000 Python tasks, which cost more than the
+    writes themselves."""
     global _filler
     from concurrent.futures import ThreadPoolExecutor
     nthreads = _fill_threads()
     if _filler is None:
         _filler = ThreadPoolExecutor(max_workers=nthreads, thread_name_prefix="b200-fill")
-    width = host3.shape[-1]
-
-    lib = _lib.load()
-    nb = host3.shape[0]
-    is_f32 = host3.element_size() == 4 and host3.dtype.is_floating_point
-
-    def rect(r0, n, c0, nc):
-        if nc <= 0:
-            return
-        if is_f32:      # non-temporal stores from the library's host helper (ctypes releases the GIL)
-            for b in range(nb):
-                _lib.check(lib.b200_host_fill_f32(host3[b, r0, c0:].data_ptr(), width, nc, n, float(value)))
-        else:
-            host3[:, r0:r0 + n, c0:c0 + nc].fill_(value)
-
-    def work(r0, n, c_lo, c_hi):
-        if c_hi <= c_lo:
-            rect(r0, n, 0, width)
-            return
-        rect(r0, n, 0, c_lo)
-        rect(r0, n, c_hi, width - c_hi)
-    futures = []
+    nb, rows, width = host3.shape
+    esize = host3.element_size()
+    is_f32 = esize == 4 and host3.dtype.is_floating_point
+    rects = []
     for r0, n, (c_lo, c_hi) in bands:
-        step = max(1, -(-n // nthreads))
+        if n <= 0:
+            continue
+        if c_hi <= c_lo:
+            rects.append((r0, n, 0, width))
+            continue
+        if c_lo > 0:
+            rects.append((r0, n, 0, c_lo))
+        if c_hi < width:
+            rects.append((r0, n, c_hi, width - c_hi))
+    total = sum(n * nc for _, n, _, nc in rects)
+    target = max(1 << 16, total // (4 * nthreads) + 1)     # elements per task
+    tasks, cur, cur_size = [], [], 0
+    for r0, n, c0, nc in rects:
+        step = max(1, min(n, target // max(1, nc)))
         for q in range(r0, r0 + n, step):
-            futures.append(_filler.submit(work, q, min(step, r0 + n - q), c_lo, c_hi))
+            m = min(step, r0 + n - q)
+            cur.append((q, m, c0, nc))
+            cur_size += m * nc
+            if cur_size >= target:
+                tasks.append(cur)
+                cur, cur_size = [], 0
+    if cur:
+        tasks.append(cur)
+    lib = _lib.load()
+    base = host3.data_ptr()
+    fvalue = float(value)
+
+    def work(batch):
+        for r0, n, c0, nc in batch:
+            if is_f32:      # non-temporal stores from the library's host helper (ctypes releases the GIL)
+                for b in range(nb):
+                    _lib.check(lib.b200_host_fill_f32(base + ((b * rows + r0) * width + c0) * 4, width, nc, n, fvalue))
+            else:
+                host3[:, r0:r0 + n, c0:c0 + nc].fill_(value)
+    futures = [_filler.submit(work, batch) for batch in tasks]
 
     class _All:
         @staticmethod

@@ -48,6 +48,7 @@ LOG = logging.getLogger(__name__)
 
 SEARCH_METHODS = {"auto": 0, "bucket": 1, "fixed_grid": 2, "fixed_grid_strict": 3}
 NN_LIGHT = 0x100   # B200_NN_LIGHT (include/satpy_b200.h)
+_PLAN_CACHE = {}   # row bands and reachable-column spans of host results, per (geometries, rows, radius)
 
 NN_COORDINATES = {"valid_input_index": ("y1", "x1"),
                   "valid_output_index": ("y2", "x2"),
@@ -107,7 +108,7 @@ class B200NearestResampler(_compat.resampler_base()):
     """Nearest-neighbour resampling on one B200."""
 
     ROW_CHUNKS = 24  # host results: rows are produced in this many bands, each copied out while the next is computed
-    SPAN_ROWS = 208  # host results: rows per reachable-column span (one device->host copy each; 8 per band of config 5)
+    SPAN_ROWS = 416  # host results: rows per reachable-column span (one device->host copy each; 4 per band of config 5)
     trace = None     # set to a list to collect (stage, start event, end event) of the fused path (bench.py)
 
     def __init__(self, source_geo_def, target_geo_def):
@@ -357,19 +358,30 @@ class B200NearestResampler(_compat.resampler_base()):
         from .. import parallel
         host_t, host_arr = _xfer.host_empty(out.shape, out.dtype)
         width = out.shape[-1]
-        bands = []
-        for r0, n in self._row_bands(nrows, True):
-            # the span is taken per SUB-band of ~SPAN_ROWS rows: a band of config 5 is 7.5 degrees of latitude, over
-            # which the disk's outline moves by up to 25 degrees of longitude; one span per band shipped 5.8 GB for
-            # 4.7 GB of disk
-            subs = []
-            for s0 in range(0, n, self.SPAN_ROWS):
-                sn = min(self.SPAN_ROWS, n - s0)
-                span = (0, width)
-                if radius is not None and out.dtype == torch.float32:
-                    span = parallel.block_column_span(self.source_geo_def, self.target_geo_def, row0 + r0 + s0, sn, radius)
-                subs.append((r0 + s0, sn, span))
-            bands.append((r0, n, subs))
+        spans_wanted = radius is not None and out.dtype == torch.float32
+        try:
+            key = (hash(self.source_geo_def), hash(self.target_geo_def), row0, nrows, radius if spans_wanted else None,
+                   self.ROW_CHUNKS, self.SPAN_ROWS)
+            bands = _PLAN_CACHE.get(key)
+        except TypeError:
+            key, bands = None, None
+        if bands is None:
+            bands = []
+            for r0, n in self._row_bands(nrows, True):
+                # the span is taken per SUB-band of SPAN_ROWS rows: a band of config 5 is 7.5 degrees of latitude, over
+                # which the disk's outline moves by up to 25 degrees of longitude
+                subs = []
+                for s0 in range(0, n, self.SPAN_ROWS):
+                    sn = min(self.SPAN_ROWS, n - s0)
+                    span = (0, width)
+                    if spans_wanted:
+                        span = parallel.block_column_span(self.source_geo_def, self.target_geo_def, row0 + r0 + s0, sn, radius)
+                    subs.append((r0 + s0, sn, span))
+                bands.append((r0, n, subs))
+            if key is not None:
+                if len(_PLAN_CACHE) > 64:
+                    _PLAN_CACHE.clear()
+                _PLAN_CACHE[key] = bands
         h3 = host_t.reshape(-1, nrows, width)
         total = nrows * width
         spanned = sum(sn * max(0, sp[1] - sp[0]) for _, _, subs in bands for _, sn, sp in subs)
@@ -388,20 +400,17 @@ class B200NearestResampler(_compat.resampler_base()):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         cs.wait_event(ev)
-        width = out3.shape[-1]
+        nb, rows, width = out3.shape
         esize = out3.element_size()
-        lib = None
-        with torch.cuda.stream(cs):
-            for s0, sn, (c_lo, c_hi) in subs:
-                if c_hi <= c_lo:
-                    continue
-                if (c_lo, c_hi) == (0, width):
-                    h3[:, s0:s0 + sn].copy_(out3[:, s0:s0 + sn], non_blocking=True)
-                    continue
-                lib = lib or _lib.load()
-                for b in range(out3.shape[0]):
-                    _lib.check(lib.b200_copy_2d(h3[b, s0, c_lo:].data_ptr(), width * esize, out3[b, s0, c_lo:].data_ptr(),
-                                                width * esize, (c_hi - c_lo) * esize, sn, int(cs.cuda_stream)))
+        lib = _lib.load()
+        hbase, dbase, stream = h3.data_ptr(), out3.data_ptr(), int(cs.cuda_stream)
+        for s0, sn, (c_lo, c_hi) in subs:
+            if c_hi <= c_lo:
+                continue
+            for b in range(nb):
+                off = ((b * rows + s0) * width + c_lo) * esize
+                _lib.check(lib.b200_copy_2d(hbase + off, width * esize, dbase + off, width * esize, (c_hi - c_lo) * esize, sn,
+                                            stream))
 
     def _row_bands(self, nrows, to_host):
         width = self.target_geo_def.width
