@@ -89,19 +89,44 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """``nvidia-smi -lms 100`` beside the run.  It is started BEFORE the warm-up and the run waits for its first sample:
+    the tool's start-up initialises the driver for every GPU of the box and can hold CUDA calls of other processes for
+    seconds (one ``--steps 1`` run of round 2 measured a 19.6 s step that way); the samples that count are the ones
+    whose time stamps fall into the timed region (``mark_start`` / ``mark_end``), or, when the region is shorter than
+    the sampling period, the samples taken under the same load just around it."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, wait_s=30.0):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+        end = time.time() + wait_s
+        while self.proc is not None and time.time() < end and self.proc.poll() is None:
+            if os.path.getsize(self.tmp.name) > 0:
+                break
+            time.sleep(0.05)
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime as _dt
+        try:
+            return _dt.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         if self.proc is None:
@@ -113,28 +138,35 @@ class ClockSampler:
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, smax, power, reasons = [], [], [], set()
+        rows = []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.tmp.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-                power.append(float(parts[2]))
+                rows.append((self._stamp(parts[0]), float(parts[1]), float(parts[2]), float(parts[3]),
+                             {name for name, val in zip(names, parts[4:8]) if val.lower().startswith("active")}))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         self.tmp.close()
         os.unlink(self.tmp.name)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None
+                  and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:      # region shorter than the sampling period: the samples just around it (same load: warm-up)
+            near = [r for r in rows if r[0] is not None and self.t0 is not None and abs(r[0] - self.t0) <= 0.35]
+            pmax = max(r[3] for r in rows)
+            inside = near or [r for r in rows if r[3] > 0.5 * pmax] or rows
+            window = "within 0.35 s of the timed region (warm-up and timed steps run the same work)"
+        reasons = set()
+        for r in inside:
+            reasons |= r[4]
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "reasons": sorted(reasons), "samples": len(inside), "samples_total": len(rows), "window": window,
+                "power_w_max": float(max(r[3] for r in inside))}
 
 
 # ---------------------------------------------------------------------------- CPU reference arm
@@ -398,12 +430,18 @@ def run_b200(args):
         return ms / max(1, steps)
 
     warm = max(3, args.warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # before the warm-up: see the class docstring
     for _ in range(warm):
         step()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if peer_image is not None:
         peer_image.bytes_pushed = 0
+    if sampler:
+        torch.cuda.synchronize()
+        sampler.mark_start()
     ms_step = timed(step, args.steps)
+    if sampler:
+        torch.cuda.synchronize()
+        sampler.mark_end()
     pushed = peer_image.bytes_pushed // max(1, args.steps) if peer_image is not None else 0
     clocks = sampler.stop() if sampler else None
     launches = LAUNCHES_PER_BLOCK * sum(1 for blk in blocks if blk.nrows and blk.s_nrows)
