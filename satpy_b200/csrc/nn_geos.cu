@@ -451,9 +451,15 @@ __device__ __forceinline__ int nn_fixed_search(const GeosDev &G, float fc, float
         nn_key_track<9u>(G, p10, txf, tyf, tzf, m1, m2);
         nn_key_track<10u>(G, p11, txf, tyf, tzf, m1, m2);
     }
+#ifndef GEOS_NO_PREFETCH
+    // the caller walks down the target rows of a tile: the next target's block is this one or the one below, whose
+    // lower row is the only line not loaded yet -- ask for it now (interior block: row r0 + 2 exists)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(q1 + G.W));
+#endif
     // best distance so far: at most sqrt(m1) + 1 m (+ the key's four bits), never more than the radius (NaN: no valid
     // pixel in the block -> fminf keeps the radius)
-    const float bd = fminf(G.radius_f, nn_sqrt_approx(__uint_as_float(m1)) + (GEOS_F32_ERR + 0.01f));
+    float s1 = nn_sqrt_approx(__uint_as_float(m1));   // (recomputed after tier 2, which may lower m1)
+    const float bd = fminf(G.radius_f, s1 + (GEOS_F32_ERR + 0.01f));
     const float wq = bd * G.inv_step * 1.0001f;
     const float fx = fc - (float)c0, fy = fr - (float)r0;
     const float edge = fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy));
@@ -486,12 +492,12 @@ __device__ __forceinline__ int nn_fixed_search(const GeosDev &G, float fc, float
             nn_key_track<14u>(G, d2, txf, tyf, tzf, m1, m2);
             nn_key_track<15u>(G, d3, txf, tyf, tzf, m1, m2);
         }
+        s1 = nn_sqrt_approx(__uint_as_float(m1));
     }
     if (m1 >= GEOS_KEY_INF) {
         GEOS_CNT(10);
         return -1;  // no valid pixel within reach
     }
-    const float s1 = nn_sqrt_approx(__uint_as_float(m1));
     const float t = s1 + (2.0f * GEOS_F32_ERR + 0.02f);
     const bool clear_winner = m2 > __float_as_uint(t * t * 1.000001f);
     const bool clear_radius = fabsf(s1 - G.radius_f) > GEOS_F32_ERR + 0.02f;
@@ -740,11 +746,12 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
             float pend_v = 0.0f;
             int pend_k = -1;
             float *const out0 = FUSED1 ? Q.O.out + i_first : nullptr;
-            for (int k = 0; k < count; ++k) {
+            const TgtRow *Rp = Q.rows + r_first;
+            unsigned vm = vmask;
+            for (int k = 0; k < count; ++k, ++Rp, vm >>= 1) {
                 int found = -1;
-                if ((vmask >> k) & 1u) {
+                if (vm & 1u) {
                     // {dlam, rc, rs} of the row: one 128-bit load, the same address for every lane
-                    const TgtRow *Rp = Q.rows + r_first + k;
                     const double2 rw = __ldg(reinterpret_cast<const double2 *>(&Rp->dlam));
                     const float rc = __int_as_float(__double2loint(rw.y)), rs = __int_as_float(__double2hiint(rw.y));
                     float fc, fr, kf;
@@ -764,7 +771,7 @@ nn_fixed_query_rect_kernel(const __grid_constant__ GeosQueryArg Q, unsigned long
                     pend_v = found < 0 ? Q.O.fill : __ldg(Q.O.data + found);
                 } else {
                     b200_nn_emit(Q.O, Q.G.prefix, i_first + (int64_t)k * W, (long long)found,
-                                 ok && ((vmask >> k) & 1u ? true : Q.rows[r_first + k].valid != 0));
+                                 ok && (vm & 1u ? true : Rp->valid != 0));
                 }
             }
             if (FUSED1 && pend_k >= 0) st_stream_f1(out0 + pend_k * W, pend_v);
