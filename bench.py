@@ -263,10 +263,10 @@ def config_dict(sp, dp, radius, args, exchange=None):
 
 # ------------------------------------------------------------------------------------ GPU arm
 # Launches of THIS repository's kernels per row block and step on the plug-in path (kernel names in the library):
-#   calibrate_abi            abi_calibrate_vec_kernel                                           1
+#   calibrate_abi            abi_calibrate_lane_kernel                                          1
 #   SunZenithCorrector       geos_tables_kernel + sunz_fast_kernel                              2
-#   B200NearestResampler     geos_tables_kernel + nn_source_points_kernel (grid build; the two prefix scans are cub's)
-#                            + nn_target_tables_kernel + nn_seg_cmax_kernel + nn_fixed_query_rect_kernel   5
+#   B200NearestResampler     geos_tables_kernel + nn_source_points_kernel (light search structure: float32 points, no
+#                            prefix scans) + nn_target_tables_kernel + nn_seg_cmax_kernel + nn_fixed_query_rect_kernel   5
 LAUNCHES_PER_BLOCK = 8
 
 

@@ -211,6 +211,7 @@ extern "C" int b200_nn_grid_destroy(b200_nn_grid_t *grid) {
     if (grid->pts) cudaFreeAsync(grid->pts, s);
     if (grid->pts32) cudaFreeAsync(grid->pts32, s);
     if (grid->prefix) cudaFreeAsync(grid->prefix, s);
+    b200_geos_fast_release(&grid->fast, s);
     cudaSetDevice(prev);
     delete grid;
     return B200_OK;
@@ -334,10 +335,11 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
         NN_TRY(cudaStreamSynchronize(s));  // h_off is pageable: finish before freeing it
         NN_TRY(cudaMallocAsync((void **)&cell_of, (size_t)n_src * sizeof(int32_t), s));
     }
-    if (!g->light) NN_TRY(cudaMallocAsync((void **)&rec, (size_t)n_src * sizeof(double4), s));
-    if (!bucket) NN_TRY(cudaMallocAsync((void **)&g->pts32, (size_t)n_src * sizeof(float4), s));
     rc = b200_geos_fast_prepare(src, &fast, s);
     if (rc) goto fail;
+    if (!fast.enabled) g->light = 0;   // (a light structure recomputes exact points from these tables)
+    if (!g->light) NN_TRY(cudaMallocAsync((void **)&rec, (size_t)n_src * sizeof(double4), s));
+    if (!bucket) NN_TRY(cudaMallocAsync((void **)&g->pts32, (size_t)n_src * sizeof(float4), s));
     if (fast.enabled)
         nn_source_points_kernel<true><<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(
             S, mask, valid_input, rec, g->pts32, cell_of, g->band_off, phi0, inv_dphi, nbands, fast);
@@ -345,6 +347,10 @@ static int nn_build(b200_nn_grid *g, const b200_geo_t *src, const uint8_t *mask,
         nn_source_points_kernel<false><<<b200_grid_for(n_src, 256, 8), 256, 0, s>>>(
             S, mask, valid_input, rec, g->pts32, cell_of, g->band_off, phi0, inv_dphi, nbands, fast);
     NN_TRY(cudaGetLastError());
+    if (g->light && fast.enabled) {   // the tables stay with the structure
+        g->fast = fast;
+        memset(&fast, 0, sizeof(fast));
+    }
     b200_geos_fast_release(&fast, s);
     if (g->light) {   // fused path: no compressed indices are ever asked for -- no prefix table, no count
         g->valid_input = valid_input;

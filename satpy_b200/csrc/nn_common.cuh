@@ -2,6 +2,7 @@
 #pragma once
 #include "b200_common.cuh"
 #include "b200_proj.cuh"
+#include "b200_geos_fast.cuh"
 
 #define B200_R_EARTH 6370997.0  // pyresample's sphere (kd_tree / geometry module constant)
 #define B200_TWO_PI 6.283185307179586476925287
@@ -37,6 +38,8 @@ struct b200_nn_grid {
     int32_t *cell_start;  // [ncells + 1] first record of each cell
     // ---- fixed-grid mode: the source area itself is the index
     b200_geo_t src;
+    GeosFast fast;        // light structures: the projection tables stay with the grid (the exact search recomputes
+                          // float64 points from them), released by b200_nn_grid_destroy
 };
 
 // Per-column / per-row quantities of a target whose lon depends on the column only and whose lat depends on the row

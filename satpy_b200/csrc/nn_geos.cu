@@ -790,19 +790,11 @@ static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst
 
 int b200_nn_fixed_grid_query(const b200_nn_grid *g, const b200_geo_t *dst, double radius, const QueryOut &O,
                              cudaStream_t s) {
-    GeosFast fast;
-    memset(&fast, 0, sizeof(fast));
-    if (g->light) {
-        if (O.index_array) {
-            b200_set_error("b200_nn_query: a light search structure (fused path) has no compressed index table");
-            return B200_EUNSUPPORTED;
-        }
-        int rc = b200_geos_fast_prepare(&g->src, &fast, s);   // the exact path recomputes float64 points from these
-        if (rc) return rc;
+    if (g->light && O.index_array) {
+        b200_set_error("b200_nn_query: a light search structure (fused path) has no compressed index table");
+        return B200_EUNSUPPORTED;
     }
-    const int rc = nn_fixed_grid_query_impl(g, dst, radius, O, s, fast);
-    if (g->light) b200_geos_fast_release(&fast, s);
-    return rc;
+    return nn_fixed_grid_query_impl(g, dst, radius, O, s, g->fast);   // (all zero for a full structure)
 }
 
 static int nn_fixed_grid_query_impl(const b200_nn_grid *g, const b200_geo_t *dst, double radius, const QueryOut &O,

@@ -8,6 +8,7 @@ python bench.py > gpurun_out/r02_final_bench_n1.json 2> gpurun_out/r02_final_ben
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_final_bench_reference.json 2> gpurun_out/r02_final_bench_reference.err
 python scripts/variant_bench.py --out gpurun_out/r02_variant_bench.json > gpurun_out/r02_variant_bench.log 2>&1
 python scripts/sunz_bench.py > gpurun_out/r02_sunz_bench.log 2>&1
+bash scripts/query_knobs.sh > gpurun_out/r02_query_knobs.txt 2>&1
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/ncu1.log 2>&1
@@ -17,6 +18,7 @@ ls -la gpurun_out/*.ncu-rep
 python -c "
 import json
 d=json.load(open('gpurun_out/r02_final_bench_n1.json'))
-print(d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['e2e']['value'], d['parity'])
+print(d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['e2e']['value'], d['parity'], d['clocks'])
 for k,v in d['stages'].items(): print(k, round(v['ms'],3), round(v['gbs'],1))
 "
+cat gpurun_out/r02_query_knobs.txt

@@ -21,8 +21,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STEP_KERNELS = ("geos_tables_kernel", "abi_calibrate_lane_kernel<0>", "sunz_fast_kernel<0, 1>", "nn_source_points_kernel<1>",
-                "DeviceScanInitKernel", "DeviceScanKernel", "nn_target_tables_kernel", "nn_seg_cmax_kernel",
-                "nn_fixed_query_rect_kernel<1>")
+                "nn_target_tables_kernel", "nn_seg_cmax_kernel", "nn_fixed_query_rect_kernel<1>")
 METRICS = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "launch__registers_per_thread", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
