@@ -41,6 +41,36 @@ def copy_stream():
     return _state(torch)["d2h"]
 
 
+class CopyStreams:
+    """The side streams the resamplers queue their device->host band copies on: ``B200_D2H_STREAMS`` of them, used
+    in turn (default 1: two or three streams measured the same 116.8 ms per call on config 5)."""
+
+    def __init__(self):
+        import os
+        torch = _lib.require_cuda()
+        st = _state(torch)
+        n = max(1, min(4, int(os.environ.get("B200_D2H_STREAMS", "1"))))
+        while len(st.setdefault("d2h_more", [])) < n - 1:
+            st["d2h_more"].append(torch.cuda.Stream())
+        self.streams = [st["d2h"]] + st["d2h_more"][:n - 1]
+        self._turn = 0
+
+    def wait_event(self, ev):
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def next(self):
+        s = self.streams[self._turn % len(self.streams)]
+        self._turn += 1
+        return s
+
+    def finish(self, tensor):
+        for s in self.streams:
+            tensor.record_stream(s)
+        for s in self.streams:
+            s.synchronize()
+
+
 def host_empty(shape, dtype):
     """``(pinned torch tensor, numpy view of it)``: the numpy array keeps the block alive; when it is dropped the
     block goes back to PyTorch's pinned-memory cache."""
@@ -54,7 +84,7 @@ _FILL_THREADS = None
 
 
 def _fill_threads():
-    """Host threads for ``fill_async``: the cores this process may use, shared between the ranks of one box, at most 16
+    """Host threads for ``fill_async``: the cores this process may use, shared between the ranks of one box, at most 6
     (``torch.set_num_threads`` / OMP_NUM_THREADS do not matter: torchrun pins them to 1)."""
     global _FILL_THREADS
     if _FILL_THREADS is None:
@@ -64,7 +94,9 @@ def _fill_threads():
         except AttributeError:
             cores = os.cpu_count() or 1
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-        _FILL_THREADS = max(1, min(16, cores // local_world))
+        # six: measured on config 5 (scripts/e2e_probe.py) -- 4 and 6 threads finish the fill well inside the copy time
+        # and leave the copies 3-4 % faster than 16 or 32 do (111.6 / 114.4 ms per call against 116.8 / 117.1)
+        _FILL_THREADS = max(1, min(6, cores // local_world))
         if os.environ.get("B200_FILL_THREADS"):        # measurements (scripts/e2e_probe.py)
             _FILL_THREADS = max(1, int(os.environ["B200_FILL_THREADS"]))
     return _FILL_THREADS

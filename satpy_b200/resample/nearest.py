@@ -403,14 +403,14 @@ class B200NearestResampler(_compat.resampler_base()):
         nb, rows, width = out3.shape
         esize = out3.element_size()
         lib = _lib.load()
-        hbase, dbase, stream = h3.data_ptr(), out3.data_ptr(), int(cs.cuda_stream)
+        hbase, dbase = h3.data_ptr(), out3.data_ptr()
         for s0, sn, (c_lo, c_hi) in subs:
             if c_hi <= c_lo:
                 continue
             for b in range(nb):
                 off = ((b * rows + s0) * width + c_lo) * esize
                 _lib.check(lib.b200_copy_2d(hbase + off, width * esize, dbase + off, width * esize, (c_hi - c_lo) * esize, sn,
-                                            stream))
+                                            int(cs.next().cuda_stream)))
 
     def _row_bands(self, nrows, to_host):
         width = self.target_geo_def.width
@@ -467,7 +467,7 @@ class B200NearestResampler(_compat.resampler_base()):
             host_t, host_arr, h3, bands, fut = self._host_plan(torch, out, cur["row_window"][0], nrows,
                                                                cur.get("radius") if np_dtype == np.float32 else None,
                                                                float(fill) if np_dtype.kind == "f" else 0)
-            cs = _xfer.copy_stream()
+            cs = _xfer.CopyStreams()
         out3 = out.reshape(nbands, nrows, width)
         for r0, n, span in bands:
             _lib.check(lib.b200_nn_gather(t.data_ptr(), out3[0, r0].data_ptr(), gi[r0].data_ptr(), n * width, nbands,
@@ -476,8 +476,7 @@ class B200NearestResampler(_compat.resampler_base()):
             if to_host:
                 self._band_to_host(torch, cs, h3, out3, r0, n, span)
         if to_host:
-            out.record_stream(cs)
-            cs.synchronize()
+            cs.finish(out)
             fut.result()
         return self._finish(data, out, host_arr)
 
@@ -566,7 +565,7 @@ class B200NearestResampler(_compat.resampler_base()):
         _t1 = _time.perf_counter()
         if to_host:
             host_t, host_arr, h3, bands, fut = self._host_plan(torch, out, row0, nrows, radius, float(fill_value))
-            cs = _xfer.copy_stream()
+            cs = _xfer.CopyStreams()
         _t2 = _time.perf_counter()
         out3 = out.reshape(nbands, nrows, width)
         stream = _lib.stream_ptr(torch)
@@ -584,8 +583,7 @@ class B200NearestResampler(_compat.resampler_base()):
         del grid   # stream-ordered: freed after the queries queued above
         _t3 = _time.perf_counter()
         if to_host:
-            out.record_stream(cs)
-            cs.synchronize()
+            cs.finish(out)
             _t4 = _time.perf_counter()
             fut.result()
             if _tr:

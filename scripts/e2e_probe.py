@@ -28,7 +28,7 @@ def step():
     return res.data, rs.last_d2h_bytes
 
 
-CASES = ((24, 208), (24, 1 << 20)) if os.environ.get('B200_FILL_THREADS') else ((24, 208), (24, 416), (24, 1 << 20), (12, 208), (48, 208))
+CASES = ((24, 416),) if (os.environ.get('B200_FILL_THREADS') or os.environ.get('B200_D2H_STREAMS')) else ((24, 208), (24, 416), (24, 1 << 20), (12, 208), (48, 208))
 for chunks, span_rows in CASES:
     B200NearestResampler.ROW_CHUNKS, B200NearestResampler.SPAN_ROWS = chunks, span_rows
     for _ in range(2):
