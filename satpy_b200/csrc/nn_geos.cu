@@ -15,13 +15,20 @@
 //        0.975 * g * pixel_size   metres
 // away (pixel_size = h * angular step, the projection-coordinate step).  The search therefore projects the
 // target into the source grid (float32 is ample: only the lattice position is needed, the margin below
-// absorbs 0.02 pixel of error), examines the 2x2 enclosing pixels with exact float64 distances (all eight
-// 128-bit loads in flight together) and then only the lattice points inside the disc of radius
-// best_distance / (0.975 * pixel_size) pixels around (fc, fr): typically 4 to 8 distance evaluations per
-// target, no build step beyond one pass that stores the source points, no sort, no cell tables.
+// absorbs 0.02 pixel of error), ranks the 2x2 enclosing pixels and then only the lattice points inside the disc of
+// radius best_distance / (0.975 * pixel_size) pixels around (fc, fr): no build step beyond one pass that stores the
+// source points, no sort, no cell tables.  Three layers decide a target (each only passes on what it cannot settle):
+//   nn_fixed_search          float32 ranking over FIXED stencils (2x2 block, 4x4 window) under the bound above sharpened
+//                            by the satellite distance of the target -- every nearest-neighbour configuration of
+//                            BASELINE.json ends here for 99.7 % of its targets;
+//   nn_fixed_refine          near-ties re-ranked in float64 from float32 points + their packed rounding residuals
+//                            (0.5 mm points);
+//   nn_fixed_search_exact    float64 points, ties to the lowest index;
+// nn_fixed_search_general is the loop of the first release (any radius, grid borders, strict mode).
 // Hidden (far-side) targets are rejected from the sign of the visibility term with a margin of 1.5 radii.
-// Rectilinear targets are processed through a dynamic work queue so that all blocks sweep one compact front of
-// target rows: the source records they share then stay in L2 although per-item cost varies 10x (on/off disk).
+// Rectilinear targets are processed in warp-sized tiles handed out by a dynamic work queue so that all warps sweep one
+// compact front of target rows: the source records they share then stay in L2 although the cost per tile varies 10x
+// (on / off the disk).
 #include "nn_common.cuh"
 #include "b200_geos_fast.cuh"
 #include "b200_bulk.cuh"

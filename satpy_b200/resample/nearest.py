@@ -178,8 +178,10 @@ class B200NearestResampler(_compat.resampler_base()):
         memory on this instance; with ``cache_dir`` it is also written to / read from ``nn_lut-<hash>.zarr`` in the
         reference's layout (kdtree.py:125-177).  ``method``: ``"auto"`` (fixed-grid search for geostationary area
         sources, bucket grid otherwise), ``"bucket"``, ``"fixed_grid"`` or ``"fixed_grid_strict"``; the engines are
-        tested to return identical indices (``fixed_grid`` rules lattice points out with a local model of the grid
-        whose margins are empirical; ``fixed_grid_strict`` examines every point of the rigorous search disc).
+        tested to return identical indices (``fixed_grid`` settles radii of up to ~2 source pixels with fixed 2x2 / 4x4
+        stencils under a rigorous distance bound and larger ones with a loop that rules lattice points out by a local
+        model of the grid with measured margins; ``fixed_grid_strict`` examines every point of the rigorous search
+        disc).
         ``gather_only``: keep just the raw gather index (what ``compute`` needs), not the reference's three arrays.
         """
         del kwargs

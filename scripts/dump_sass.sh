@@ -7,7 +7,9 @@ set -e
 ROUND=${1:-r02}
 LIB=satpy_b200/libsatpy_b200.so
 declare -A K=(
-  [nn_fixed_query_rect_fused]=_Z26nn_fixed_query_rect_kernelILb1EEv12GeosQueryArgPyPKf
+  [nn_fixed_query_rect_fused]=_Z26nn_fixed_query_rect_kernelILb1EEv12GeosQueryArgPyPKfjji
+  [nn_source_points_fast]=_Z23nn_source_points_kernelILb1EEv6SrcArgPKhPhP7double4P6float4PiPKiddi8GeosFast
+  [bil_sample_bulk]=_Z22bil_sample_bulk_kernelPKfPfPKiPKdS5_lf
   [sunz_fast_f32]=_Z16sunz_fast_kernelILi0ELb1EEv11SunzFastArg7SunzDev
   [sunz_fast_fused_abi]=_Z16sunz_fast_kernelILi1ELb1EEv11SunzFastArg7SunzDev
   [abi_calibrate_lane]=_Z25abi_calibrate_lane_kernelILb0EEvPKsPfl9AbiCalDev
@@ -23,7 +25,7 @@ for name in "${!K[@]}"; do
   n=$(grep -c '^\s*/\*[0-9a-f]\{4\}\*/' $out || true)
   echo "" >> $CENSUS
   echo "$name (${K[$name]}): $n instructions" >> $CENSUS
-  for m in UBLKCP SYNCS UTMALDG UTMASTG "LDG.E.128" "LDG.E.64" "STG.E.128" "STG.E.NA.128" "LDG.E.NA.64" LDS STS MUFU DFMA DMUL F2F I2F "FFMA" BSSY; do
+  for m in UBLKCP SYNCS UTMALDG UTMASTG CCTL VIMNMX LOP3 "LDG.E.128" "LDG.E.64" "STG.E.128" "STG.E.NA.128" "LDG.E.NA.64" LDS STS MUFU DFMA DMUL F2F I2F "FFMA" BSSY; do
     c=$(grep -c "$m" $out || true)
     [ "$c" != "0" ] && echo "    $m: $c" >> $CENSUS
   done
