@@ -569,3 +569,57 @@ def test_block_column_span_is_conservative():
     laea = demo.make_area("euro_laea_1km", 0.05)
     assert parallel.block_column_span(src, laea, 0, 10, radius) == (0, laea.width)
     assert parallel.block_column_span(laea, dst, 0, 10, radius) == (0, dst.width)
+
+
+# ------------------------------------------------------------------ host side of the transfers (no device needed)
+def test_fill_async_writes_exactly_the_outside_of_the_spans():
+    """``_xfer.fill_async`` (the library's host helper with non-temporal stores, a few batched tasks per thread): the
+    columns outside every band's span get the fill value, the spans and the rows of no band are not touched."""
+    import torch
+    from satpy_b200 import _xfer
+    rng = np.random.default_rng(3)
+    nb, rows, width = 2, 97, 1013
+    host = torch.from_numpy(rng.random((nb, rows, width), dtype=np.float32))
+    before = host.numpy().copy()
+    bands = [(0, 10, (100, 900)), (10, 30, (0, 0)), (40, 7, (0, width)), (47, 40, (3, 1013)), (87, 5, (512, 513))]
+    _xfer.fill_async(host, [b for b in bands if b[2] != (0, width)], float("nan")).result()
+    got = host.numpy()
+    expect = before.copy()
+    for r0, n, (lo, hi) in bands:
+        if hi <= lo:
+            expect[:, r0:r0 + n] = np.nan
+        else:
+            expect[:, r0:r0 + n, :lo] = np.nan
+            expect[:, r0:r0 + n, hi:] = np.nan
+    np.testing.assert_array_equal(got, expect)          # rows 92..96 belong to no band: untouched
+    assert np.isfinite(got[:, 92:]).all()
+    # integer images take the generic path
+    u8 = torch.zeros((1, 16, 64), dtype=torch.uint8)
+    _xfer.fill_async(u8, [(0, 16, (8, 24))], 255).result()
+    assert (u8.numpy()[0, :, :8] == 255).all() and (u8.numpy()[0, :, 24:] == 255).all() and (u8.numpy()[0, :, 8:24] == 0).all()
+
+
+def test_threaded_host_copy_is_a_memcpy():
+    from satpy_b200 import _xfer
+    a = np.random.default_rng(4).integers(0, 255, size=(9 << 20) + 13, dtype=np.uint8)
+    b = np.zeros_like(a)
+    _xfer._host_copy(b.ctypes.data, a.ctypes.data, a.nbytes)
+    np.testing.assert_array_equal(a, b)
+    c = np.zeros(1000, np.uint8)
+    _xfer._host_copy(c.ctypes.data, a.ctypes.data, 1000)       # small: single memmove
+    np.testing.assert_array_equal(c, a[:1000])
+
+
+def test_row_bands_cover_any_width_on_multiples_of_four_rows():
+    """Host results are produced in row bands whatever the width (config 5's 80150 columns are not a multiple of 4):
+    bands tile the rows exactly and start on multiples of four rows (16-byte boundaries of the output rows)."""
+    from satpy_b200 import demo
+    from satpy_b200.resample import B200NearestResampler
+    src, dst = demo.make_area("goes_east_abi_f_1km"), demo.make_area("global_eqc_500m")
+    r = B200NearestResampler(src, dst)
+    for nrows in (dst.height, 5010, 1253, 3, 0):
+        bands = r._row_bands(nrows, True)
+        assert sum(n for _, n in bands) == nrows
+        assert all(r0 % 4 == 0 for r0, _ in bands)
+        assert [r0 for r0, _ in bands] == list(np.cumsum([0] + [n for _, n in bands])[:-1])
+    assert len(r._row_bands(dst.height, True)) == 24 and len(r._row_bands(dst.height, False)) == 1
