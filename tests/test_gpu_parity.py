@@ -245,7 +245,11 @@ def _assert_sunz_close(res, ref, data=None, cz=None, max_sza=None, limit=88.0):
             sliver = cz < np.cos(np.deg2rad(max_sza - 0.25))
         tol = np.where(sliver, REL * np.abs(data) / np.cos(np.deg2rad(limit)) + 1e-6, tol)
     bad = ok & (err > tol)
-    assert not bad.any(), f"{bad.sum()} pixels outside tolerance, worst {np.nanmax(np.where(ok, err / tol, 0)):.2f} x tol"
+    # how many pixels only pass because of the absolute bar of the sliver (the tolerance north_star does not grant)
+    needed_abs = int((ok & (err > REL * np.abs(ref) + 1e-6) & ~bad).sum())
+    assert not bad.any(), (f"{bad.sum()} pixels outside tolerance, worst {np.nanmax(np.where(ok, err / tol, 0)):.2f} x tol; "
+                           f"{needed_abs} of {int(ok.sum())} pixels needed the absolute bar of the last 0.25 degree")
+    return needed_abs
 
 
 @pytest.mark.parametrize("areaname,scale,when", [
@@ -263,7 +267,8 @@ def test_sunz_correct_matches_oracle(areaname, scale, when, max_sza, limit):
     ref = osolar.sun_zenith_corrector(data, oarea, when, correction_limit=limit, max_sza=max_sza)
     cz = osolar.get_cos_sza(oarea, when, np.float32)
     assert res.dtype == np.float32
-    _assert_sunz_close(res, ref, data, cz, max_sza, limit)
+    needed_abs = _assert_sunz_close(res, ref, data, cz, max_sza, limit)
+    assert needed_abs <= 2e-3 * res.size, f"{needed_abs} pixels needed the absolute bar before max_sza"   # the sliver only
     # multi-band input shares the factor
     res3 = sunz_correct(np.stack([data, data * 2]), area=area, start_time=when, correction_limit=limit,
                         max_sza=max_sza)
