@@ -526,9 +526,9 @@ def run_b200(args):
             vin.precompute(radius_of_influence=radius, row_window=(0, 1))
             n_valid = int(vin._current["n_valid"])
             del vin
-        alg = {"calibrate": ("abi_calibrate_vec_kernel (reflectance)", 6 * n_src_win),
+        alg = {"calibrate": ("abi_calibrate_lane_kernel (reflectance)", 6 * n_src_win),
                "sunz_correct": ("sunz_fast_kernel<0> (+ geos_tables_kernel)", 8 * n_src_win),
-               "build": ("nn_source_points_kernel + prefix scans (search structure)", 0),
+               "build": ("geos_tables_kernel + nn_source_points_kernel (light search structure: float32 points)", 17 * n_src_win),
                "query_gather": ("nn_fixed_query_rect_kernel (fused query+gather)", 4 * n_out_mine + 4 * n_valid)}
         for name, pairs in acc.items():
             ms = float(sum(a.elapsed_time(b) for a, b in pairs)) / max(1, args.steps)   # per step, over this rank's blocks
@@ -685,7 +685,7 @@ def standalone_stages(torch, args, src, dst, counts, radius, blk0):
     out = torch.empty(src.shape, dtype=torch.float32, device="cuda")
     for band, calib in (("C02", "radiance"), ("C02", "reflectance"), ("C13", "brightness_temperature")):
         cal = demo.abi_calibration(band)
-        stage(f"calibrate_{calib}", "abi_calibrate_vec_kernel", lambda: calibrate_abi(cdev, cal, calib, out=out), 6 * n,
+        stage(f"calibrate_{calib}", "abi_calibrate_lane_kernel", lambda: calibrate_abi(cdev, cal, calib, out=out), 6 * n,
               f"ABI {band} 10848^2")
     refl = torch.rand(src.shape, device="cuda") * 100
     stage("sunz_correct_standalone", "sunz_fast_kernel<0>", lambda: sunz_correct(refl, area=src, start_time=demo.START_TIME, out=out),
