@@ -252,13 +252,14 @@ class PeerImage:
         # the fill (one bandwidth-bound launch over everything outside the spans) runs at normal priority: issued after
         # the last block's search it takes the SM slots that kernel's tail leaves and overlaps the last pushes
         self.fill_stream = torch.cuda.Stream()
-        # "burst" mode (B200_EXCHANGE_MODE=burst; the default from 8 ranks on): one barrier per push, then the copies
+        # "burst" mode (B200_EXCHANGE_MODE=burst; the default from 4 ranks on): one barrier per push, then the copies
         # to all peers at once on their own streams -- every rank sends 1/(N-1) of its egress to every peer and receives
         # the same from each, so the switch is loaded evenly without a barrier per round (28 barriers of ~0.1 ms per
         # step at N = 8 against pushes of 0.23 ms).  "rounds": the lock-step rotation described above.
         import os
         mode = os.environ.get("B200_EXCHANGE_MODE", "auto")
-        self.burst = mode == "burst" or (mode == "auto" and self.world >= 8)
+        # N = 4, final round-2 library: burst 9.10 ms per step, rounds 9.44 ms (both verified; different boxes of the pool)
+        self.burst = mode == "burst" or (mode == "auto" and self.world >= 4)
         self.peer_streams = [torch.cuda.Stream(priority=-1) for _ in range(self.world - 1)] if self.burst else []
         self.trace = None  # set to a list to collect (peer, row0, nbytes, start event, end event) per copy
         self.bytes_pushed = 0   # payload this rank sent since the counter was last reset (bench.py reports it)
