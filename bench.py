@@ -98,7 +98,7 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, wait_s=30.0):
+    def __init__(self, index, wait_s=20.0):   # below PeerImage.BARRIER_TIMEOUT_MS: the other ranks wait in their first barrier
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
         self.t0 = self.t1 = None
